@@ -1,0 +1,181 @@
+/*
+ * splacu.h -- C ABI of the B200-native (sm_100a) backend for spla's masked semiring
+ * matrix-vector hot path: exec_mxv_masked (pull) and exec_vxm_masked (push / SpMSpV).
+ *
+ * This is the drop-in boundary. Everything above it (spla's Matrix/Vector/Scalar objects, the
+ * algorithm registry, the storage manager) stays the reference's own host code; the C++ plug-in
+ * that a spla maintainer adds in src/cuda (shipped here under spla_b200/src/cuda) includes ONLY
+ * this header and never a CUDA header. Plain pointers and sizes, no C++/torch types.
+ *
+ * Conventions
+ *   - every value is 4 bytes (spla T_INT / T_UINT / T_FLOAT, reference src/type.cpp:32-35);
+ *     scalars cross the ABI as raw uint32_t bit patterns, arrays as void* device pointers
+ *   - `d_` pointers are device memory, `h_` pointers host memory
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the backend's own stream); calls only
+ *     ENQUEUE work unless documented to synchronise, like the reference's in-order OpenCL queue
+ *     (reference src/opencl/cl_accelerator.hpp:81)
+ *   - return 0 on success, a SPLACU_E_* code (< 0) or a cudaError_t (> 0) otherwise;
+ *     splacu_last_error() gives the message. Nothing throws across this boundary.
+ *   - there is NO CPU fallback behind any entry point.
+ */
+#ifndef SPLACU_H
+#define SPLACU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define SPLACU_API __attribute__((visibility("default")))
+
+/* ---- enums mirroring the reference's built-ins ------------------------------------------- */
+
+/* value types, reference src/type.cpp:32-35 */
+typedef enum splacu_dtype { SPLACU_INT = 0, SPLACU_UINT = 1, SPLACU_FLOAT = 2 } splacu_dtype;
+
+/* built-in binary ops in the order of reference src/op.cpp:194-241 (TOpBinary names) */
+typedef enum splacu_binop {
+    SPLACU_PLUS = 0, SPLACU_MINUS, SPLACU_MULT, SPLACU_DIV, SPLACU_MINUS_POW2, SPLACU_FIRST, SPLACU_SECOND,
+    SPLACU_BONE, SPLACU_MIN, SPLACU_MAX, SPLACU_LOR, SPLACU_LAND, SPLACU_BOR, SPLACU_BAND, SPLACU_BXOR,
+    SPLACU_BINOP_COUNT
+} splacu_binop;
+
+/* built-in select ops in the order of reference src/op.cpp:243-266 (TOpSelect names) */
+typedef enum splacu_selop {
+    SPLACU_EQZERO = 0, SPLACU_NQZERO, SPLACU_GTZERO, SPLACU_GEZERO, SPLACU_LTZERO, SPLACU_LEZERO,
+    SPLACU_ALWAYS, SPLACU_NEVER, SPLACU_SELOP_COUNT
+} splacu_selop;
+
+enum {
+    SPLACU_OK               = 0,
+    SPLACU_E_INVALID        = -1, /* bad argument (null pointer, unknown op, op not defined for dtype) */
+    SPLACU_E_NOT_INIT       = -2, /* splacu_init not called / no CUDA device */
+    SPLACU_E_CAPACITY       = -3, /* caller-provided output buffer too small; required size reported */
+    SPLACU_E_NOT_IMPLEMENTED = -4 /* user-defined (non built-in) op: no device code available */
+};
+
+/* ---- runtime: replaces reference src/opencl/cl_accelerator.{hpp,cpp} (CLAccelerator::init,
+ *      set_device, queue creation :84-201) ---------------------------------------------------- */
+
+SPLACU_API int         splacu_init(int device);              /* cudaSetDevice + backend stream + scratch pool */
+SPLACU_API int         splacu_finalize(void);
+SPLACU_API int         splacu_device_count(int* count);
+SPLACU_API int         splacu_device_name(char* buffer, int length);
+SPLACU_API int         splacu_sm_count(int* count);
+SPLACU_API void*       splacu_default_stream(void);          /* the backend's own in-order stream */
+SPLACU_API int         splacu_sync(void* stream);            /* cudaStreamSynchronize */
+SPLACU_API const char* splacu_last_error(void);
+SPLACU_API int         splacu_launch_count(uint64_t* count); /* kernels launched by this library so far */
+
+/* device memory: replaces cl::Buffer creation / enqueueRead / enqueueWrite in
+ * reference src/opencl/cl_format_dense_vec.hpp:43-87, cl_format_coo_vec.hpp:43-125, cl_format_csr.hpp:40-96 */
+SPLACU_API int splacu_malloc(void** d_ptr, size_t bytes);
+SPLACU_API int splacu_free(void* d_ptr);
+SPLACU_API int splacu_malloc_host(void** h_ptr, size_t bytes); /* pinned staging memory */
+SPLACU_API int splacu_free_host(void* h_ptr);
+SPLACU_API int splacu_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);  /* async */
+SPLACU_API int splacu_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);  /* async; sync before reading */
+SPLACU_API int splacu_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
+/* replaces kernels fill_zero / fill_value, reference src/opencl/kernels/fill.cl:30,41 (cl_fill.hpp) */
+SPLACU_API int splacu_fill(void* d_dst, uint32_t value_bits, size_t n, void* stream);
+
+/* ---- device CSR matrix: replaces CLCsr + cl_csr_init, reference src/opencl/cl_formats.hpp:93-103,
+ *      cl_format_csr.hpp:40-63. The handle does not own Ap/Aj/Ax; it owns the load-balancing
+ *      metadata built once per matrix (decorations may carry extra data, core/accelerator.hpp:50-52). */
+
+typedef struct splacu_csr_t* splacu_csr;
+
+SPLACU_API int splacu_csr_create(splacu_csr* M, uint32_t n_rows, uint32_t n_cols, uint32_t nnz,
+                                 const uint32_t* d_Ap, const uint32_t* d_Aj, const void* d_Ax, void* stream);
+SPLACU_API int splacu_csr_destroy(splacu_csr M);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+
+/* Pull: r[i] = select(mask[i]) ? fold_{(j,a) in row i, stored order}(add, init, mult(a, v[j])) : init
+ * Replaces Algo_mxv_masked_cl<T>::execute (reference src/opencl/cl_mxv.hpp:65-246, kernels/mxv.cl:43-170);
+ * semantics are those of Algo_mxv_masked_cpu<T>::execute (reference src/cpu/cpu_mxv.hpp:56-106):
+ * every r[i] written, mult(a_ij, v_j) argument order, early_exit = stop at the first position where
+ * the running sum != init. d_v has n_cols entries, d_mask and d_r n_rows entries.
+ * Results: bit-exact for INT/UINT, for MIN/MAX/logical/bitwise ops and for early_exit with any op;
+ * FLOAT PLUS/MULT reductions differ from the sequential fold only by summation order. */
+SPLACU_API int splacu_mxv_masked(splacu_csr M, int dtype, int op_mult, int op_add, int op_select,
+                                 const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits,
+                                 int early_exit, void* stream);
+
+/* Per-vector-length scratch for vxm / compaction (dense accumulator, touched bitmap, scan buffers).
+ * Replaces the temp linear allocator + counters of reference src/opencl/cl_alloc_linear.hpp, cl_counter.hpp:42-84. */
+typedef struct splacu_workspace_t* splacu_workspace;
+SPLACU_API int splacu_workspace_create(splacu_workspace* ws);
+SPLACU_API int splacu_workspace_destroy(splacu_workspace ws);
+
+/* Push (SpMSpV): for every stored (i,x) of sparse v, for (j,a) in row i with select(mask[j]):
+ *   acc[j] = first ? mult(x,a) : add(acc[j], mult(x,a));  result = touched (j, acc[j]) ascending in j.
+ * Replaces Algo_vxm_masked_cl<T>::execute_sparse (reference src/opencl/cl_vxm.hpp:73-180,
+ * kernels/vxm.cl:30-95, cl_sort_by_key.hpp, cl_reduce_by_key.hpp); semantics are those of
+ * Algo_vxm_masked_cpu<T>::execute (reference src/cpu/cpu_vxm.hpp:58-128): init is ignored, the output
+ * pattern is structural (touched columns stay even if the value equals the fill value).
+ * d_vi/d_vx: nv frontier entries; d_mask: n_cols entries.
+ *
+ * Two-phase form (what the spla plug-in uses, because TDecoration::values is a host uint,
+ * reference src/core/tdecoration.hpp:58):
+ *   splacu_vxm_masked_begin   accumulates on the device and returns the result count in *h_nr
+ *                             (ONE 4-byte device->host synchronisation; the reference's OpenCL path has 2-3)
+ *   splacu_vxm_masked_emit    writes the ordered (ri, rx) pairs into exactly-sized buffers and resets the scratch
+ */
+SPLACU_API int splacu_vxm_masked_begin(splacu_csr M, int dtype, int op_mult, int op_add, int op_select,
+                                       uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
+                                       splacu_workspace ws, uint32_t* h_nr, void* stream);
+SPLACU_API int splacu_vxm_masked_emit(splacu_workspace ws, uint32_t* d_ri, void* d_rx, void* stream);
+
+/* One-call form over caller-provided buffers of `capacity` entries (n_cols always suffices). */
+SPLACU_API int splacu_vxm_masked(splacu_csr M, int dtype, int op_mult, int op_add, int op_select,
+                                 uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
+                                 uint32_t* d_ri, void* d_rx, uint32_t capacity, uint32_t* h_nr,
+                                 splacu_workspace ws, void* stream);
+
+/* ---- vector format glue: replaces kernels sparse_to_dense / dense_to_sparse,
+ *      reference src/opencl/kernels/vector_formats.cl:30,42 (cl_format_coo_vec.hpp:127-161,
+ *      cl_format_dense_vec.hpp:89-143). dense_to_coo keeps ascending index order like the CPU
+ *      converter (reference src/cpu/cpu_format_dense_vec.hpp:53-67), which the OpenCL kernel does not. */
+SPLACU_API int splacu_coo_to_dense(uint32_t n, uint32_t fill_bits, uint32_t nv, const uint32_t* d_vi, const void* d_vx,
+                                   void* d_dense, void* stream);
+SPLACU_API int splacu_dense_to_coo_count(int dtype, uint32_t n, uint32_t fill_bits, const void* d_dense,
+                                         splacu_workspace ws, uint32_t* h_nr, void* stream);
+SPLACU_API int splacu_dense_to_coo_emit(int dtype, uint32_t n, uint32_t fill_bits, const void* d_dense,
+                                        splacu_workspace ws, uint32_t* d_ri, void* d_rx, void* stream);
+
+/* ---- neighbours of the hot path inside bfs / sssp / pr loops -------------------- */
+
+/* r[i] = select(mask[i]) ? assign(r[i], value) : r[i]; reference src/cpu/cpu_v_assign.hpp:95-127,
+ * replaces src/opencl/cl_v_assign.hpp + kernels/vector_assign.cl:30 */
+SPLACU_API int splacu_v_assign_masked_dense(int dtype, int op_assign, int op_select, uint32_t n,
+                                            void* d_r, const void* d_mask, uint32_t value_bits, void* stream);
+/* sparse mask: for every stored (i,x) with select(x): r[i] = assign(r[i], value);
+ * reference src/cpu/cpu_v_assign.hpp:66-93, kernels/vector_assign.cl:44 */
+SPLACU_API int splacu_v_assign_masked_sparse(int dtype, int op_assign, int op_select,
+                                             void* d_r, uint32_t nm, const uint32_t* d_mi, const void* d_mx,
+                                             uint32_t value_bits, void* stream);
+/* number of entries != fill; reference src/cpu/cpu_v_count_mf.hpp:91-107, kernels/count.cl:46. Synchronises. */
+SPLACU_API int splacu_v_count_mf_dense(int dtype, uint32_t n, const void* d_v, uint32_t fill_bits,
+                                       splacu_workspace ws, uint32_t* h_count, void* stream);
+/* r[i] = op(r[i], v[i]); fdb[i] = changed ? r[i] : fdb_fill; reference src/cpu/cpu_v_eadd_fdb.hpp:104-137 */
+SPLACU_API int splacu_v_eadd_fdb_dense(int dtype, int op, uint32_t n, void* d_r, const void* d_v,
+                                       void* d_fdb, uint32_t fdb_fill_bits, void* stream);
+/* sparse v -> sparse feedback in the order of v; reference src/cpu/cpu_v_eadd_fdb.hpp:70-102.
+ * v indices must be unique (they are: vxm output). Two-phase like vxm. */
+SPLACU_API int splacu_v_eadd_fdb_sparse_begin(int dtype, int op, void* d_r, uint32_t nv, const uint32_t* d_vi,
+                                              const void* d_vx, splacu_workspace ws, uint32_t* h_nf, void* stream);
+SPLACU_API int splacu_v_eadd_fdb_sparse_emit(splacu_workspace ws, uint32_t* d_fi, void* d_fx, void* stream);
+/* r[i] = op(u[i], v[i]); reference src/cpu/cpu_v_eadd.hpp:128-152 */
+SPLACU_API int splacu_v_eadd_dense(int dtype, int op, uint32_t n, void* d_r, const void* d_u, const void* d_v, void* stream);
+/* s = fold(op, init, v); reference src/cpu/cpu_v_reduce.hpp:90-114. Synchronises. op must be associative
+ * and commutative (PLUS, MULT, MIN, MAX, LOR, LAND, BOR, BAND, BXOR); FLOAT PLUS/MULT differ by summation order. */
+SPLACU_API int splacu_v_reduce_dense(int dtype, int op, uint32_t n, const void* d_v, uint32_t init_bits,
+                                     splacu_workspace ws, uint32_t* h_result_bits, void* stream);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* SPLACU_H */

@@ -1,0 +1,292 @@
+"""Host-side Python binding of the splacu C ABI (include/splacu.h) for the bench harness and the parity tests.
+
+The product is the CUDA library; this module only marshals device pointers. torch is plumbing here (device
+memory, streams, torch.distributed) -- no arithmetic of the hot path happens in torch, and there is NO fallback:
+if libsplacu.so is missing or no CUDA device is present, construction fails loudly.
+
+The call surface mirrors the reference's own entry points for the path:
+    Backend.mxv_masked(...)  <->  spla::exec_mxv_masked / spla_Exec_mxv_masked  (reference include/spla/exec.hpp:157-167, include/spla.h:372)
+    Backend.vxm_masked(...)  <->  spla::exec_vxm_masked / spla_Exec_vxm_masked  (reference include/spla/exec.hpp:187-197, include/spla.h:373)
+with the same argument meaning (r, mask, M, v, op_multiply, op_add, op_select, init, desc.early_exit).
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+INT, UINT, FLOAT = 0, 1, 2
+
+BIN_OPS = ["PLUS", "MINUS", "MULT", "DIV", "MINUS_POW2", "FIRST", "SECOND", "BONE",
+           "MIN", "MAX", "LOR", "LAND", "BOR", "BAND", "BXOR"]
+SEL_OPS = ["EQZERO", "NQZERO", "GTZERO", "GEZERO", "LTZERO", "LEZERO", "ALWAYS", "NEVER"]
+BIN = {n: i for i, n in enumerate(BIN_OPS)}
+SEL = {n: i for i, n in enumerate(SEL_OPS)}
+
+# every symbol include/splacu.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "splacu_init", "splacu_finalize", "splacu_device_count", "splacu_device_name", "splacu_sm_count",
+    "splacu_default_stream", "splacu_sync", "splacu_last_error", "splacu_launch_count",
+    "splacu_malloc", "splacu_free", "splacu_malloc_host", "splacu_free_host",
+    "splacu_memcpy_h2d", "splacu_memcpy_d2h", "splacu_memcpy_d2d", "splacu_fill",
+    "splacu_csr_create", "splacu_csr_destroy", "splacu_mxv_masked",
+    "splacu_workspace_create", "splacu_workspace_destroy",
+    "splacu_vxm_masked_begin", "splacu_vxm_masked_emit", "splacu_vxm_masked",
+    "splacu_coo_to_dense", "splacu_dense_to_coo_count", "splacu_dense_to_coo_emit",
+    "splacu_v_assign_masked_dense", "splacu_v_assign_masked_sparse", "splacu_v_count_mf_dense",
+    "splacu_v_eadd_fdb_dense", "splacu_v_eadd_fdb_sparse_begin", "splacu_v_eadd_fdb_sparse_emit",
+    "splacu_v_eadd_dense", "splacu_v_reduce_dense",
+]
+
+
+class SplacuError(RuntimeError):
+    pass
+
+
+def load_library(build_if_missing=True):
+    """dlopen spla_b200/lib/libsplacu.so; build it with nvcc first if it is not there. Never falls back."""
+    path = _build.LIB
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise SplacuError(f"{path} is missing: run `python -m spla_b200.build`")
+        _build.build_splacu()
+    lib = C.CDLL(path)
+    vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
+    pu32 = C.POINTER(C.c_uint32)
+    sig = {
+        "splacu_init": [i32], "splacu_finalize": [], "splacu_device_count": [C.POINTER(C.c_int)],
+        "splacu_device_name": [C.c_char_p, i32], "splacu_sm_count": [C.POINTER(C.c_int)],
+        "splacu_sync": [vp], "splacu_launch_count": [C.POINTER(C.c_uint64)],
+        "splacu_malloc": [C.POINTER(vp), sz], "splacu_free": [vp],
+        "splacu_malloc_host": [C.POINTER(vp), sz], "splacu_free_host": [vp],
+        "splacu_memcpy_h2d": [vp, vp, sz, vp], "splacu_memcpy_d2h": [vp, vp, sz, vp], "splacu_memcpy_d2d": [vp, vp, sz, vp],
+        "splacu_fill": [vp, u32, sz, vp],
+        "splacu_csr_create": [C.POINTER(vp), u32, u32, u32, vp, vp, vp, vp], "splacu_csr_destroy": [vp],
+        "splacu_mxv_masked": [vp, i32, i32, i32, i32, vp, vp, vp, u32, i32, vp],
+        "splacu_workspace_create": [C.POINTER(vp)], "splacu_workspace_destroy": [vp],
+        "splacu_vxm_masked_begin": [vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, pu32, vp],
+        "splacu_vxm_masked_emit": [vp, vp, vp, vp],
+        "splacu_vxm_masked": [vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, vp, u32, pu32, vp, vp],
+        "splacu_coo_to_dense": [u32, u32, u32, vp, vp, vp, vp],
+        "splacu_dense_to_coo_count": [i32, u32, u32, vp, vp, pu32, vp],
+        "splacu_dense_to_coo_emit": [i32, u32, u32, vp, vp, vp, vp, vp],
+        "splacu_v_assign_masked_dense": [i32, i32, i32, u32, vp, vp, u32, vp],
+        "splacu_v_assign_masked_sparse": [i32, i32, i32, vp, u32, vp, vp, u32, vp],
+        "splacu_v_count_mf_dense": [i32, u32, vp, u32, vp, pu32, vp],
+        "splacu_v_eadd_fdb_dense": [i32, i32, u32, vp, vp, vp, u32, vp],
+        "splacu_v_eadd_fdb_sparse_begin": [i32, i32, vp, u32, vp, vp, vp, pu32, vp],
+        "splacu_v_eadd_fdb_sparse_emit": [vp, vp, vp, vp],
+        "splacu_v_eadd_dense": [i32, i32, u32, vp, vp, vp, vp],
+        "splacu_v_reduce_dense": [i32, i32, u32, vp, u32, vp, pu32, vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.splacu_default_stream.argtypes = []
+    lib.splacu_default_stream.restype = C.c_void_p
+    lib.splacu_last_error.argtypes = []
+    lib.splacu_last_error.restype = C.c_char_p
+    return lib
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return FLOAT
+    if t.dtype == torch.int32:
+        return INT
+    if t.dtype == torch.uint32:
+        return UINT
+    raise TypeError(f"spla values are 4-byte INT/UINT/FLOAT, got {t.dtype}")
+
+
+def scalar_bits(code, x):
+    if code == FLOAT:
+        return int(torch.tensor([float(x)], dtype=torch.float32).view(torch.int32).item()) & 0xFFFFFFFF
+    return int(x) & 0xFFFFFFFF
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class CsrMatrix:
+    """Device-resident CSR (Ap uint32[n_rows+1], Aj uint32[nnz], Ax T[nnz]) plus the backend's load-balancing
+    metadata; the counterpart of the reference's CLCsr decoration (src/opencl/cl_formats.hpp:93-103)."""
+
+    def __init__(self, backend, n_rows, n_cols, Ap, Aj, Ax):
+        assert Ap.is_cuda and Aj.is_cuda and Ax.is_cuda
+        assert Ap.dtype == torch.int32 and Aj.dtype == torch.int32 and Ap.numel() == n_rows + 1
+        self.backend, self.n_rows, self.n_cols = backend, n_rows, n_cols
+        self.Ap, self.Aj, self.Ax = Ap.contiguous(), Aj.contiguous(), Ax.contiguous()
+        self.nnz = Aj.numel()
+        self.dtype = dtype_code(Ax)
+        h = C.c_void_p()
+        backend._check(backend.lib.splacu_csr_create(C.byref(h), n_rows, n_cols, self.nnz, _ptr(self.Ap), _ptr(self.Aj),
+                                                     _ptr(self.Ax), backend.stream_ptr))
+        self.handle = h
+
+    def __del__(self):
+        if getattr(self, "handle", None) is not None:
+            try:
+                self.backend.lib.splacu_csr_destroy(self.handle)
+            except Exception:
+                pass
+            self.handle = None
+
+
+class Backend:
+    """One backend per process / GPU (one process per GPU under torch.distributed)."""
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise SplacuError("spla_b200 needs a CUDA device: there is no CPU fallback on this path")
+        self.lib = load_library()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self._check(self.lib.splacu_init(device))
+        sp = self.lib.splacu_default_stream()
+        self.stream_ptr = C.c_void_p(sp)
+        self.stream = torch.cuda.ExternalStream(sp, device=self.device)
+        ws = C.c_void_p()
+        self._check(self.lib.splacu_workspace_create(C.byref(ws)))
+        self.ws = ws
+        self._nr = C.c_uint32(0)
+
+    # ---- plumbing ----
+    def _check(self, rc):
+        if rc != 0:
+            raise SplacuError(f"splacu error {rc}: {self.lib.splacu_last_error().decode()}")
+
+    def sync(self):
+        self._check(self.lib.splacu_sync(self.stream_ptr))
+
+    def launch_count(self):
+        c = C.c_uint64(0)
+        self.lib.splacu_launch_count(C.byref(c))
+        return c.value
+
+    def device_name(self):
+        buf = C.create_string_buffer(256)
+        self.lib.splacu_device_name(buf, 256)
+        return buf.value.decode()
+
+    def csr(self, n_rows, n_cols, Ap, Aj, Ax):
+        with torch.cuda.stream(self.stream):
+            return CsrMatrix(self, n_rows, n_cols, Ap, Aj, Ax)
+
+    def empty(self, n, like=None, dtype=torch.float32):
+        with torch.cuda.stream(self.stream):
+            return torch.empty(n, dtype=like.dtype if like is not None else dtype, device=self.device)
+
+    # ---- the hot path ----
+    def mxv_masked(self, M, v, mask, op_mult, op_add, op_select, init, early_exit=False, out=None):
+        """r = M x v (pull). Mirrors exec_mxv_masked(r, mask, M, v, op_multiply, op_add, op_select, init, desc)."""
+        code = M.dtype
+        assert v.numel() == M.n_cols and dtype_code(v) == code
+        if mask is not None:
+            assert mask.numel() == M.n_rows and dtype_code(mask) == code
+        if out is None:
+            out = self.empty(M.n_rows, like=v)
+        self._check(self.lib.splacu_mxv_masked(M.handle, code, BIN[op_mult], BIN[op_add], SEL[op_select], _ptr(v), _ptr(mask),
+                                               _ptr(out), scalar_bits(code, init), int(bool(early_exit)), self.stream_ptr))
+        return out
+
+    def vxm_masked(self, M, vi, vx, mask, op_mult, op_add, op_select, out=None):
+        """r = v x M (push) over the sparse vector (vi, vx). Mirrors exec_vxm_masked(r, mask, v, M, ...).
+        Returns (ri, rx) exactly-sized (or views of `out=(ri_buf, rx_buf)`)."""
+        code = M.dtype
+        nv = vi.numel()
+        assert vx.numel() == nv and (nv == 0 or dtype_code(vx) == code) and vi.dtype == torch.int32
+        if mask is not None:
+            assert mask.numel() == M.n_cols and dtype_code(mask) == code
+        self._check(self.lib.splacu_vxm_masked_begin(M.handle, code, BIN[op_mult], BIN[op_add], SEL[op_select], nv, _ptr(vi), _ptr(vx),
+                                                     _ptr(mask), self.ws, C.byref(self._nr), self.stream_ptr))
+        nr = self._nr.value
+        if out is not None:
+            ri, rx = out[0][:nr], out[1][:nr]
+        else:
+            with torch.cuda.stream(self.stream):
+                ri = torch.empty(nr, dtype=torch.int32, device=self.device)
+                rx = torch.empty(nr, dtype=M.Ax.dtype, device=self.device)
+        self._check(self.lib.splacu_vxm_masked_emit(self.ws, _ptr(ri), _ptr(rx), self.stream_ptr))
+        return ri, rx
+
+    # ---- format glue ----
+    def coo_to_dense(self, n, fill, vi, vx, out=None):
+        code = dtype_code(vx)
+        if out is None:
+            out = self.empty(n, like=vx)
+        self._check(self.lib.splacu_coo_to_dense(n, scalar_bits(code, fill), vi.numel(), _ptr(vi), _ptr(vx), _ptr(out), self.stream_ptr))
+        return out
+
+    def dense_to_coo(self, dense, fill):
+        code = dtype_code(dense)
+        n = dense.numel()
+        fb = scalar_bits(code, fill)
+        self._check(self.lib.splacu_dense_to_coo_count(code, n, fb, _ptr(dense), self.ws, C.byref(self._nr), self.stream_ptr))
+        nr = self._nr.value
+        with torch.cuda.stream(self.stream):
+            ri = torch.empty(nr, dtype=torch.int32, device=self.device)
+            rx = torch.empty(nr, dtype=dense.dtype, device=self.device)
+        self._check(self.lib.splacu_dense_to_coo_emit(code, n, fb, _ptr(dense), self.ws, _ptr(ri), _ptr(rx), self.stream_ptr))
+        return ri, rx
+
+    def fill(self, t, value):
+        self._check(self.lib.splacu_fill(_ptr(t), scalar_bits(dtype_code(t), value), t.numel(), self.stream_ptr))
+        return t
+
+    # ---- neighbours ----
+    def v_assign_masked(self, r, mask, value, op_assign, op_select):
+        """dense mask: exec_v_assign_masked(r, mask, value, op_assign, op_select); mask may be (mi, mx) sparse."""
+        code = dtype_code(r)
+        vb = scalar_bits(code, value)
+        if isinstance(mask, tuple):
+            mi, mx = mask
+            self._check(self.lib.splacu_v_assign_masked_sparse(code, BIN[op_assign], SEL[op_select], _ptr(r), mi.numel(), _ptr(mi), _ptr(mx),
+                                                               vb, self.stream_ptr))
+        else:
+            self._check(self.lib.splacu_v_assign_masked_dense(code, BIN[op_assign], SEL[op_select], r.numel(), _ptr(r), _ptr(mask), vb,
+                                                              self.stream_ptr))
+        return r
+
+    def v_count_mf(self, v, fill):
+        code = dtype_code(v)
+        self._check(self.lib.splacu_v_count_mf_dense(code, v.numel(), _ptr(v), scalar_bits(code, fill), self.ws, C.byref(self._nr), self.stream_ptr))
+        return self._nr.value
+
+    def v_eadd_fdb_dense(self, r, v, op, fdb_fill, fdb=None):
+        code = dtype_code(r)
+        if fdb is None:
+            fdb = self.empty(r.numel(), like=r)
+        self._check(self.lib.splacu_v_eadd_fdb_dense(code, BIN[op], r.numel(), _ptr(r), _ptr(v), _ptr(fdb), scalar_bits(code, fdb_fill), self.stream_ptr))
+        return fdb
+
+    def v_eadd_fdb_sparse(self, r, vi, vx, op):
+        code = dtype_code(r)
+        self._check(self.lib.splacu_v_eadd_fdb_sparse_begin(code, BIN[op], _ptr(r), vi.numel(), _ptr(vi), _ptr(vx), self.ws, C.byref(self._nr),
+                                                            self.stream_ptr))
+        nf = self._nr.value
+        with torch.cuda.stream(self.stream):
+            fi = torch.empty(nf, dtype=torch.int32, device=self.device)
+            fx = torch.empty(nf, dtype=r.dtype, device=self.device)
+        self._check(self.lib.splacu_v_eadd_fdb_sparse_emit(self.ws, _ptr(fi), _ptr(fx), self.stream_ptr))
+        return fi, fx
+
+    def v_eadd(self, u, v, op, out=None):
+        code = dtype_code(u)
+        if out is None:
+            out = self.empty(u.numel(), like=u)
+        self._check(self.lib.splacu_v_eadd_dense(code, BIN[op], u.numel(), _ptr(out), _ptr(u), _ptr(v), self.stream_ptr))
+        return out
+
+    def v_reduce(self, v, op, init):
+        code = dtype_code(v)
+        self._check(self.lib.splacu_v_reduce_dense(code, BIN[op], v.numel(), _ptr(v), scalar_bits(code, init), self.ws, C.byref(self._nr), self.stream_ptr))
+        bits = self._nr.value
+        if code == FLOAT:
+            return float(torch.tensor([bits if bits < 2 ** 31 else bits - 2 ** 32], dtype=torch.int32).view(torch.float32).item())
+        if code == INT:
+            return bits if bits < 2 ** 31 else bits - 2 ** 32
+        return bits

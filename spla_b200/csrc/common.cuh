@@ -1,0 +1,119 @@
+// common.cuh -- shared host/device helpers of the splacu backend (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/splacu.h"
+
+namespace splacu {
+
+    // ---- error plumbing -------------------------------------------------------------------
+    void        set_error(const char* fmt, ...);
+    int         cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+    extern bool g_initialised;
+    void        count_launch(int n = 1);
+
+#define SPLACU_CUDA(expr)                                                          \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) return ::splacu::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define SPLACU_REQUIRE(cond, msg)                       \
+    do {                                                \
+        if (!(cond)) {                                  \
+            ::splacu::set_error("%s: %s", __func__, msg); \
+            return SPLACU_E_INVALID;                    \
+        }                                               \
+    } while (0)
+
+#define SPLACU_CHECK_INIT()                                               \
+    do {                                                                  \
+        if (!::splacu::g_initialised) {                                   \
+            ::splacu::set_error("%s: splacu_init() has not been called", __func__); \
+            return SPLACU_E_NOT_INIT;                                     \
+        }                                                                 \
+    } while (0)
+
+// check the launch itself (bad config etc.); execution errors surface at the next sync
+#define SPLACU_LAUNCH_CHECK()                                   \
+    do {                                                        \
+        ::splacu::count_launch();                               \
+        cudaError_t _e = cudaGetLastError();                    \
+        if (_e != cudaSuccess) return ::splacu::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+    cudaStream_t resolve_stream(void* stream);
+    int          sm_count();
+
+    // grid sized as a multiple of the SM count for grid-stride kernels
+    inline int grid_for(size_t work_items, int block, int ctas_per_sm) {
+        size_t want = (work_items + block - 1) / block;
+        size_t cap  = (size_t) sm_count() * ctas_per_sm;
+        if (want < 1) want = 1;
+        return (int) (want < cap ? want : cap);
+    }
+
+    // ---- device csr handle ---------------------------------------------------------------
+    struct Csr {
+        uint32_t        n_rows = 0, n_cols = 0, nnz = 0;
+        const uint32_t* Ap = nullptr;
+        const uint32_t* Aj = nullptr;
+        const uint32_t* Ax = nullptr;
+        // load-balancing metadata for the streaming pull kernel (mxv_pull.cu), owned
+        uint32_t  n_tiles      = 0;
+        uint32_t* tile_row     = nullptr;// [n_tiles+1] first row touching each nnz tile
+        uint32_t  max_row_nnz  = 0;
+        float     avg_row_nnz  = 0.f;
+    };
+
+    // ---- workspace ------------------------------------------------------------------------
+    struct Workspace {
+        // dense accumulator + touched bitmap (vxm), sized for the largest vector seen
+        uint32_t* acc          = nullptr;
+        uint32_t* bitmap       = nullptr;
+        uint32_t  cap_n        = 0;      // capacity in elements of acc
+        uint32_t  acc_identity = 0;      // bit pattern acc[] is currently filled with
+        bool      acc_clean    = false;  // acc[] == identity everywhere and bitmap == 0
+        // scan scratch
+        uint32_t* block_sums   = nullptr;
+        uint32_t  cap_blocks   = 0;
+        uint32_t* d_scalars    = nullptr;// small device scalars (counters, totals): 64 words
+        uint32_t* h_scalars    = nullptr;// pinned mirror
+        // generic exact vxm path buffers
+        uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr, *offsets = nullptr;
+        size_t    cap_pairs = 0, cap_offsets = 0;
+        void*     sort_tmp = nullptr;
+        size_t    cap_sort_tmp = 0;
+        // pending emit state between *_begin and *_emit
+        int       pending      = 0;      // 0 none, 1 vxm (acc/bitmap), 2 eadd_fdb sparse
+        uint32_t  pend_n       = 0;      // length of the bitmap domain
+        uint32_t  pend_count   = 0;
+        uint32_t  pend_identity = 0;
+        const uint32_t* pend_vi = nullptr;
+        const uint32_t* pend_src = nullptr;
+    };
+
+    int ws_reserve_vector(Workspace* ws, uint32_t n, cudaStream_t s);
+    int ws_reserve_blocks(Workspace* ws, uint32_t n_blocks);
+    int ws_reserve_pairs(Workspace* ws, size_t n_pairs, size_t n_offsets);
+
+    // ---- shared device-side building blocks (defined in vector_ops.cu) -----------------------
+    // exclusive scan of n uint32 (in place allowed); total written to d_total (may be null)
+    int scan_exclusive_u32(Workspace* ws, const uint32_t* d_in, uint32_t* d_out, uint32_t n, uint32_t* d_total, cudaStream_t s);
+
+    enum EmitMode {
+        EMIT_ACC_RESET = 0,// (j, src[j]); afterwards src[j] = identity, bitmap word = 0     (vxm)
+        EMIT_DENSE     = 1,// (j, src[j]); nothing reset                                      (dense -> coo)
+        EMIT_INDIRECT  = 2 // (vi[k], src[vi[k]]) for set bit k; bitmap word = 0              (eadd_fdb sparse)
+    };
+    // popcount the bitmap over [0, n) -> per-block sums scanned in ws->block_sums, total in ws->d_scalars[0]
+    int bitmap_count(Workspace* ws, const uint32_t* d_bitmap, uint32_t n, cudaStream_t s);
+    // ordered emit; requires bitmap_count() on the same bitmap before
+    int bitmap_emit(Workspace* ws, uint32_t* d_bitmap, uint32_t n, int mode, uint32_t* d_src, const uint32_t* d_vi,
+                    uint32_t identity, uint32_t* d_ri, uint32_t* d_rx, cudaStream_t s);
+
+}// namespace splacu

@@ -1,0 +1,295 @@
+// runtime.cu -- device runtime of the splacu backend: init, stream, memory, error reporting,
+// device CSR handle and workspace. Replaces the OpenCL runtime of the reference
+// (src/opencl/cl_accelerator.cpp:84-201, cl_alloc_*.cpp, cl_counter.cpp) for the hot path.
+#include "common.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+namespace splacu {
+
+    bool                  g_initialised = false;
+    static int            g_device      = -1;
+    static int            g_sm_count    = 148;
+    static cudaStream_t   g_stream      = nullptr;
+    static char           g_device_name[256] = "none";
+    static std::atomic<uint64_t> g_launches{0};
+    static thread_local char     g_error[1024] = "";
+
+    void set_error(const char* fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(g_error, sizeof(g_error), fmt, ap);
+        va_end(ap);
+    }
+
+    int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+        set_error("CUDA error %d (%s) at %s:%d: %s", (int) e, cudaGetErrorName(e), file, line, what);
+        cudaGetLastError();// clear sticky launch-config errors
+        return (int) e;
+    }
+
+    void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
+
+    cudaStream_t resolve_stream(void* stream) { return stream ? (cudaStream_t) stream : g_stream; }
+    int          sm_count() { return g_sm_count; }
+
+    int ws_reserve_vector(Workspace* ws, uint32_t n, cudaStream_t s) {
+        if (n <= ws->cap_n && ws->acc) return 0;
+        SPLACU_CUDA(cudaStreamSynchronize(s));
+        if (ws->acc) cudaFree(ws->acc);
+        if (ws->bitmap) cudaFree(ws->bitmap);
+        ws->acc = ws->bitmap = nullptr;
+        size_t cap   = (size_t) n + (n >> 2) + 1024;// head-room so that growing vectors do not thrash
+        if (cap > 0xffffffffull) cap = 0xffffffffull;
+        size_t words = (cap + 31) / 32 + 1;
+        SPLACU_CUDA(cudaMalloc(&ws->acc, cap * sizeof(uint32_t)));
+        SPLACU_CUDA(cudaMalloc(&ws->bitmap, words * sizeof(uint32_t)));
+        SPLACU_CUDA(cudaMemsetAsync(ws->bitmap, 0, words * sizeof(uint32_t), s));
+        ws->cap_n     = (uint32_t) cap;
+        ws->acc_clean = false;
+        return 0;
+    }
+
+    int ws_reserve_blocks(Workspace* ws, uint32_t n_blocks) {
+        if (n_blocks <= ws->cap_blocks && ws->block_sums) return 0;
+        if (ws->block_sums) {
+            SPLACU_CUDA(cudaDeviceSynchronize());
+            cudaFree(ws->block_sums);
+            ws->block_sums = nullptr;
+        }
+        size_t cap = (size_t) n_blocks * 2 + 1024;
+        SPLACU_CUDA(cudaMalloc(&ws->block_sums, cap * sizeof(uint32_t)));
+        ws->cap_blocks = (uint32_t) cap;
+        return 0;
+    }
+
+    int ws_reserve_pairs(Workspace* ws, size_t n_pairs, size_t n_offsets) {
+        if (n_pairs > ws->cap_pairs) {
+            SPLACU_CUDA(cudaDeviceSynchronize());
+            cudaFree(ws->keys_a); cudaFree(ws->keys_b); cudaFree(ws->vals_a); cudaFree(ws->vals_b);
+            ws->keys_a = ws->keys_b = ws->vals_a = ws->vals_b = nullptr;
+            size_t cap = n_pairs + n_pairs / 4 + 1024;
+            SPLACU_CUDA(cudaMalloc(&ws->keys_a, cap * 4));
+            SPLACU_CUDA(cudaMalloc(&ws->keys_b, cap * 4));
+            SPLACU_CUDA(cudaMalloc(&ws->vals_a, cap * 4));
+            SPLACU_CUDA(cudaMalloc(&ws->vals_b, cap * 4));
+            ws->cap_pairs = cap;
+        }
+        if (n_offsets > ws->cap_offsets) {
+            SPLACU_CUDA(cudaDeviceSynchronize());
+            cudaFree(ws->offsets);
+            ws->offsets = nullptr;
+            size_t cap  = n_offsets + n_offsets / 4 + 1024;
+            SPLACU_CUDA(cudaMalloc(&ws->offsets, cap * 4));
+            ws->cap_offsets = cap;
+        }
+        return 0;
+    }
+
+    // defined in mxv_pull.cu
+    int csr_build_metadata(Csr* M, cudaStream_t s);
+
+}// namespace splacu
+
+using namespace splacu;
+
+extern "C" {
+
+int splacu_init(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("splacu_init: no CUDA device available (%s); this backend has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return SPLACU_E_NOT_INIT;
+    }
+    if (device < 0 || device >= count) {
+        set_error("splacu_init: device %d out of range [0, %d)", device, count);
+        return SPLACU_E_INVALID;
+    }
+    SPLACU_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SPLACU_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (g_initialised && g_device == device) return SPLACU_OK;
+    if (g_stream) {
+        cudaStreamDestroy(g_stream);
+        g_stream = nullptr;
+    }
+    SPLACU_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_device   = device;
+    g_sm_count = prop.multiProcessorCount;
+    snprintf(g_device_name, sizeof(g_device_name), "%s (sm_%d%d, %d SMs, %.0f GB)", prop.name, prop.major, prop.minor,
+             prop.multiProcessorCount, (double) prop.totalGlobalMem / 1e9);
+    g_initialised = true;
+    return SPLACU_OK;
+}
+
+int splacu_finalize(void) {
+    if (g_stream) {
+        cudaStreamSynchronize(g_stream);
+        cudaStreamDestroy(g_stream);
+        g_stream = nullptr;
+    }
+    g_initialised = false;
+    g_device      = -1;
+    return SPLACU_OK;
+}
+
+int splacu_device_count(int* count) {
+    SPLACU_REQUIRE(count, "null pointer");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+    }
+    return SPLACU_OK;
+}
+
+int splacu_device_name(char* buffer, int length) {
+    SPLACU_REQUIRE(buffer && length > 0, "bad buffer");
+    snprintf(buffer, (size_t) length, "%s", g_device_name);
+    return SPLACU_OK;
+}
+
+int splacu_sm_count(int* count) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(count, "null pointer");
+    *count = g_sm_count;
+    return SPLACU_OK;
+}
+
+void* splacu_default_stream(void) { return (void*) g_stream; }
+
+int splacu_sync(void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_CUDA(cudaStreamSynchronize(resolve_stream(stream)));
+    return SPLACU_OK;
+}
+
+const char* splacu_last_error(void) { return g_error; }
+
+int splacu_launch_count(uint64_t* count) {
+    SPLACU_REQUIRE(count, "null pointer");
+    *count = g_launches.load();
+    return SPLACU_OK;
+}
+
+int splacu_malloc(void** d_ptr, size_t bytes) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(d_ptr, "null pointer");
+    *d_ptr = nullptr;
+    if (bytes == 0) bytes = 4;
+    SPLACU_CUDA(cudaMalloc(d_ptr, bytes));
+    return SPLACU_OK;
+}
+
+int splacu_free(void* d_ptr) {
+    if (!d_ptr) return SPLACU_OK;
+    // safe after splacu_finalize (reference Library::finalize destroys the accelerator while
+    // decorations may still hold device buffers, src/library.cpp:97-104): the primary context survives
+    cudaError_t e = cudaFree(d_ptr);
+    if (e != cudaSuccess && e != cudaErrorCudartUnloading) return cuda_fail(e, "cudaFree", __FILE__, __LINE__);
+    return SPLACU_OK;
+}
+
+int splacu_malloc_host(void** h_ptr, size_t bytes) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(h_ptr, "null pointer");
+    if (bytes == 0) bytes = 4;
+    SPLACU_CUDA(cudaMallocHost(h_ptr, bytes));
+    return SPLACU_OK;
+}
+
+int splacu_free_host(void* h_ptr) {
+    if (!h_ptr) return SPLACU_OK;
+    cudaError_t e = cudaFreeHost(h_ptr);
+    if (e != cudaSuccess && e != cudaErrorCudartUnloading) return cuda_fail(e, "cudaFreeHost", __FILE__, __LINE__);
+    return SPLACU_OK;
+}
+
+int splacu_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream) {
+    SPLACU_CHECK_INIT();
+    if (bytes == 0) return SPLACU_OK;
+    SPLACU_REQUIRE(d_dst && h_src, "null pointer");
+    SPLACU_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, resolve_stream(stream)));
+    return SPLACU_OK;
+}
+
+int splacu_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream) {
+    SPLACU_CHECK_INIT();
+    if (bytes == 0) return SPLACU_OK;
+    SPLACU_REQUIRE(h_dst && d_src, "null pointer");
+    SPLACU_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, resolve_stream(stream)));
+    return SPLACU_OK;
+}
+
+int splacu_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream) {
+    SPLACU_CHECK_INIT();
+    if (bytes == 0) return SPLACU_OK;
+    SPLACU_REQUIRE(d_dst && d_src, "null pointer");
+    SPLACU_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, resolve_stream(stream)));
+    return SPLACU_OK;
+}
+
+int splacu_csr_create(splacu_csr* out, uint32_t n_rows, uint32_t n_cols, uint32_t nnz,
+                      const uint32_t* d_Ap, const uint32_t* d_Aj, const void* d_Ax, void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(out, "null handle pointer");
+    SPLACU_REQUIRE(d_Ap, "null Ap");
+    SPLACU_REQUIRE(nnz == 0 || (d_Aj && d_Ax), "null Aj/Ax");
+    Csr* M    = new Csr();
+    M->n_rows = n_rows;
+    M->n_cols = n_cols;
+    M->nnz    = nnz;
+    M->Ap     = d_Ap;
+    M->Aj     = d_Aj;
+    M->Ax     = static_cast<const uint32_t*>(d_Ax);
+    int rc    = csr_build_metadata(M, resolve_stream(stream));
+    if (rc != 0) {
+        delete M;
+        return rc;
+    }
+    *out = reinterpret_cast<splacu_csr>(M);
+    return SPLACU_OK;
+}
+
+int splacu_csr_destroy(splacu_csr handle) {
+    if (!handle) return SPLACU_OK;
+    Csr* M = reinterpret_cast<Csr*>(handle);
+    if (M->tile_row) cudaFree(M->tile_row);
+    delete M;
+    return SPLACU_OK;
+}
+
+int splacu_workspace_create(splacu_workspace* out) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(out, "null handle pointer");
+    Workspace* ws = new Workspace();
+    cudaError_t e = cudaMalloc(&ws->d_scalars, 64 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&ws->h_scalars, 64 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ws->d_scalars, 0, 64 * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        delete ws;
+        return cuda_fail(e, "workspace alloc", __FILE__, __LINE__);
+    }
+    *out = reinterpret_cast<splacu_workspace>(ws);
+    return SPLACU_OK;
+}
+
+int splacu_workspace_destroy(splacu_workspace handle) {
+    if (!handle) return SPLACU_OK;
+    Workspace* ws = reinterpret_cast<Workspace*>(handle);
+    cudaFree(ws->acc); cudaFree(ws->bitmap); cudaFree(ws->block_sums); cudaFree(ws->d_scalars);
+    cudaFreeHost(ws->h_scalars);
+    cudaFree(ws->keys_a); cudaFree(ws->keys_b); cudaFree(ws->vals_a); cudaFree(ws->vals_b); cudaFree(ws->offsets);
+    cudaFree(ws->sort_tmp);
+    cudaGetLastError();
+    delete ws;
+    return SPLACU_OK;
+}
+
+}// extern "C"

@@ -1,0 +1,254 @@
+// vxm_push.cu -- masked semiring push product r = v x M over a sparse frontier (spla exec_vxm_masked, SpMSpV).
+//
+// Semantics: reference src/cpu/cpu_vxm.hpp:92-125 (see include/splacu.h). Replaces the OpenCL pipeline
+// count -> blocking read -> collect -> radix sort (6-8 passes) -> reduce-by-key -> blocking read
+// (reference src/opencl/cl_vxm.hpp:107-173) with
+//   1. degree gather + exclusive scan over the frontier            (load-balancing offsets, no host sync)
+//   2. load-balanced expand: every thread owns a contiguous run of edge slots of the expanded frontier, finds its
+//      frontier entry by binary search in the offsets, tests the mask BEFORE touching Ax, and folds the product into a
+//      dense per-vector accumulator with an op-specialised atomic; touched columns are recorded in a bitmap
+//   3. popcount + scan of the bitmap (n/8 bytes) -> result count    (the single 4-byte device->host sync)
+//   4. ordered emit of (j, acc[j]) and reset of exactly the touched scratch
+// Step 2 is exact for every associative + commutative add whose identity e satisfies add(e, x) == x
+// (PLUS, MULT, MIN, MAX, BOR, BAND, BXOR; LOR/LAND when the products are already 0/1), because the reference
+// stores the first product of a column directly. Every other op pair takes the exact ordered path:
+// expand (column, product) pairs at their deterministic frontier-order positions, stable radix sort by column,
+// strict left-to-right fold per column.
+#include "common.cuh"
+#include "ops.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace splacu {
+
+    static constexpr int kBlock = 256;
+    static constexpr int kEpt   = 8;// edge slots per thread per chunk
+
+    __global__ void __launch_bounds__(kBlock) vxm_degrees_kernel(uint32_t nv, const uint32_t* __restrict__ vi, const uint32_t* __restrict__ Ap,
+                                                                 uint32_t* __restrict__ deg) {
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nv; t += stride) {
+            const uint32_t i = vi[t];
+            deg[t]           = Ap[i + 1] - Ap[i];
+        }
+    }
+
+    // last t in [0, nv) with off[t] <= e   (off is non-decreasing, off[0] == 0 <= e)
+    __device__ __forceinline__ uint32_t find_entry(const uint32_t* __restrict__ off, uint32_t nv, uint32_t e) {
+        uint32_t lo = 0, hi = nv;// invariant: off[lo] <= e, (hi == nv or off[hi] > e)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (off[mid] <= e) lo = mid;
+            else hi = mid;
+        }
+        return lo;
+    }
+
+    // MODE 0: atomic accumulate into acc + bitmap (fast path). MODE 1: write (key, product) pairs (exact path).
+    template<typename T, typename S, int MODE>
+    __global__ void __launch_bounds__(kBlock) vxm_expand_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj,
+                                                                const T* __restrict__ Ax, uint32_t nv, const uint32_t* __restrict__ vi,
+                                                                const T* __restrict__ vx, const T* __restrict__ mask,
+                                                                const uint32_t* __restrict__ off /*[nv+1]*/, T* __restrict__ acc,
+                                                                uint32_t* __restrict__ bitmap, uint32_t* __restrict__ keys, T* __restrict__ vals,
+                                                                uint32_t invalid_key) {
+        const uint32_t total = off[nv];
+        const uint32_t chunk = kBlock * kEpt;
+        for (uint64_t base = (uint64_t) blockIdx.x * chunk; base < total; base += (uint64_t) gridDim.x * chunk) {
+            if (base + threadIdx.x * kEpt >= total) continue;
+            uint32_t e = (uint32_t) base + threadIdx.x * kEpt;
+            const uint32_t e_end = min(total, e + kEpt);
+            uint32_t       t     = find_entry(off, nv, e);
+            uint32_t       t_end = off[t + 1];
+            uint32_t       row0  = Ap[vi[t]] - off[t];// k = row0 + e
+            T              x     = vx[t];
+            for (; e < e_end; ++e) {
+                while (e >= t_end) {// next frontier entry (skips entries with empty rows)
+                    ++t;
+                    t_end = off[t + 1];
+                    row0  = Ap[vi[t]] - off[t];
+                    x     = vx[t];
+                }
+                const uint32_t k    = row0 + e;
+                const uint32_t j    = Aj[k];
+                const bool     take = sel.reads_mask ? sel.test(mask[j]) : (sel.classes != 0u);
+                if (MODE == 0) {
+                    if (take) {
+                        atomic_combine<T>(sr.add_op(), &acc[j], sr.mult(x, Ax[k]));
+                        const uint32_t bit = 1u << (j & 31u);
+                        if (!(*reinterpret_cast<volatile uint32_t*>(&bitmap[j >> 5]) & bit)) atomicOr(&bitmap[j >> 5], bit);
+                    }
+                } else {
+                    keys[e] = take ? j : invalid_key;
+                    vals[e] = take ? sr.mult(x, Ax[k]) : T(0);
+                }
+            }
+        }
+    }
+
+    // exact path: after the stable sort, the head of every key run folds its run left to right
+    template<typename T>
+    __global__ void __launch_bounds__(kBlock) vxm_fold_runs_kernel(int op_add, uint32_t n_pairs, const uint32_t* __restrict__ keys,
+                                                                   const T* __restrict__ vals, uint32_t invalid_key, T* __restrict__ acc,
+                                                                   uint32_t* __restrict__ bitmap) {
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs; q += stride) {
+            const uint32_t key = keys[q];
+            if (key == invalid_key) continue;
+            if (q > 0 && keys[q - 1] == key) continue;
+            T a = vals[q];
+            for (uint32_t p = q + 1; p < n_pairs && keys[p] == key; ++p) a = bin_dynamic<T>(op_add, a, vals[p]);
+            acc[key] = a;
+            atomicOr(&bitmap[key >> 5], 1u << (key & 31u));
+        }
+    }
+
+    static bool fast_path_ok(int op_mult, int op_add) {
+        switch (op_add) {
+            case SPLACU_PLUS: case SPLACU_MULT: case SPLACU_MIN: case SPLACU_MAX:
+            case SPLACU_BOR: case SPLACU_BAND: case SPLACU_BXOR: return true;
+            case SPLACU_LOR: case SPLACU_LAND:
+                // the reference returns the RAW product for a column with a single contribution; the accumulator
+                // normalises to 0/1, so the two agree only when products are 0/1 already
+                return op_mult == SPLACU_LOR || op_mult == SPLACU_LAND || op_mult == SPLACU_BONE;
+            default: return false;
+        }
+    }
+
+    template<typename T>
+    static int vxm_begin_typed(const Csr* M, int op_mult, int op_add, const Select& sel, uint32_t nv, const uint32_t* d_vi, const T* d_vx,
+                               const T* d_mask, Workspace* ws, uint32_t* h_nr, cudaStream_t s) {
+        const uint32_t n = M->n_cols;
+        int            rc;
+        if ((rc = ws_reserve_vector(ws, n, s))) return rc;
+        if ((rc = ws_reserve_pairs(ws, 0, (size_t) nv + 1))) return rc;
+
+        // 1. load-balancing offsets
+        vxm_degrees_kernel<<<grid_for(nv, kBlock, 8), kBlock, 0, s>>>(nv, d_vi, M->Ap, ws->offsets);
+        SPLACU_LAUNCH_CHECK();
+        if ((rc = scan_exclusive_u32(ws, ws->offsets, ws->offsets, nv, ws->offsets + nv, s))) return rc;
+
+        const bool fast     = fast_path_ok(op_mult, op_add);
+        const T    identity = fast ? add_identity<T>(op_add) : from_bits<T>(ws->acc_identity);
+        T*         acc      = reinterpret_cast<T*>(ws->acc);
+        const int  grid     = sm_count() * 8;
+
+        if (fast) {
+            if (!ws->acc_clean || ws->acc_identity != to_bits(identity)) {
+                if ((rc = splacu_fill(ws->acc, to_bits(identity), ws->cap_n, (void*) s))) return rc;
+                ws->acc_identity = to_bits(identity);
+                ws->acc_clean    = true;
+            }
+            rc = dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
+                using S = decltype(sr);
+                vxm_expand_kernel<T, S, 0><<<grid, kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vi, d_vx, d_mask,
+                                                                   ws->offsets, acc, ws->bitmap, nullptr, nullptr, 0u);
+                SPLACU_LAUNCH_CHECK();
+                return 0;
+            });
+            if (rc) return rc;
+        } else {
+            // exact ordered path: needs the pair count on the host to size the sort buffers
+            SPLACU_CUDA(cudaMemcpyAsync(ws->h_scalars + 1, ws->offsets + nv, 4, cudaMemcpyDeviceToHost, s));
+            SPLACU_CUDA(cudaStreamSynchronize(s));
+            const uint32_t n_pairs = ws->h_scalars[1];
+            if (n_pairs) {
+                if ((rc = ws_reserve_pairs(ws, n_pairs, (size_t) nv + 1))) return rc;
+                SemiringDynamic<T> sr;
+                sr.mul   = op_mult;
+                sr.ad    = op_add;
+                sr.ident = T(0);
+                vxm_expand_kernel<T, SemiringDynamic<T>, 1><<<grid, kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vi, d_vx,
+                                                                                   d_mask, ws->offsets, nullptr, nullptr, ws->keys_a,
+                                                                                   reinterpret_cast<T*>(ws->vals_a), n);
+                SPLACU_LAUNCH_CHECK();
+                int end_bit = 1;
+                while (end_bit < 32 && (n >> end_bit) != 0u) ++end_bit;// keys are in [0, n]
+                size_t tmp_bytes = 0;
+                SPLACU_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ws->keys_a, ws->keys_b, ws->vals_a, ws->vals_b, (int) n_pairs, 0, end_bit, s));
+                if (tmp_bytes > ws->cap_sort_tmp) {
+                    SPLACU_CUDA(cudaStreamSynchronize(s));
+                    cudaFree(ws->sort_tmp);
+                    ws->sort_tmp = nullptr;
+                    SPLACU_CUDA(cudaMalloc(&ws->sort_tmp, tmp_bytes + tmp_bytes / 4));
+                    ws->cap_sort_tmp = tmp_bytes + tmp_bytes / 4;
+                }
+                SPLACU_CUDA(cub::DeviceRadixSort::SortPairs(ws->sort_tmp, tmp_bytes, ws->keys_a, ws->keys_b, ws->vals_a, ws->vals_b, (int) n_pairs, 0, end_bit, s));
+                count_launch(8);
+                vxm_fold_runs_kernel<T><<<grid_for(n_pairs, kBlock, 8), kBlock, 0, s>>>(op_add, n_pairs, ws->keys_b, reinterpret_cast<const T*>(ws->vals_b), n, acc, ws->bitmap);
+                SPLACU_LAUNCH_CHECK();
+            }
+        }
+
+        // 3. count
+        if ((rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;
+        SPLACU_CUDA(cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, 4, cudaMemcpyDeviceToHost, s));
+        SPLACU_CUDA(cudaStreamSynchronize(s));
+        *h_nr             = ws->h_scalars[0];
+        ws->pending       = 1;
+        ws->pend_n        = n;
+        ws->pend_count    = *h_nr;
+        ws->pend_identity = to_bits(identity);
+        return 0;
+    }
+
+}// namespace splacu
+
+using namespace splacu;
+
+extern "C" {
+
+int splacu_vxm_masked_begin(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select,
+                            uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
+                            splacu_workspace wsh, uint32_t* h_nr, void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(handle && wsh && h_nr, "null handle");
+    const Csr* M  = reinterpret_cast<const Csr*>(handle);
+    Workspace* ws = reinterpret_cast<Workspace*>(wsh);
+    SPLACU_REQUIRE(op_valid_for(dtype, op_mult), "op_mult not defined for dtype");
+    SPLACU_REQUIRE(op_valid_for(dtype, op_add), "op_add not defined for dtype");
+    SPLACU_REQUIRE(op_select >= 0 && op_select < SPLACU_SELOP_COUNT, "unknown op_select");
+    SPLACU_REQUIRE(ws->pending == 0, "workspace has a pending emit");
+    const Select sel = make_select(op_select);
+    *h_nr            = 0;
+    if (nv == 0 || M->n_cols == 0 || M->nnz == 0 || sel.classes == 0u) return SPLACU_OK;// nothing can be touched
+    SPLACU_REQUIRE(d_vi && d_vx, "null frontier pointers");
+    SPLACU_REQUIRE(d_mask || !sel.reads_mask, "null mask pointer");
+    cudaStream_t s = resolve_stream(stream);
+    return dispatch_dtype(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        return vxm_begin_typed<T>(M, op_mult, op_add, sel, nv, d_vi, static_cast<const T*>(d_vx), static_cast<const T*>(d_mask), ws, h_nr, s);
+    });
+}
+
+int splacu_vxm_masked_emit(splacu_workspace wsh, uint32_t* d_ri, void* d_rx, void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(wsh, "null workspace");
+    Workspace* ws = reinterpret_cast<Workspace*>(wsh);
+    if (ws->pending == 0) return SPLACU_OK;// begin() short-circuited on an empty product
+    SPLACU_REQUIRE(ws->pending == 1, "vxm_masked_emit without matching begin");
+    ws->pending = 0;
+    if (ws->pend_count == 0) return SPLACU_OK;// nothing touched: scratch still clean
+    SPLACU_REQUIRE(d_ri && d_rx, "null output pointers");
+    return bitmap_emit(ws, ws->bitmap, ws->pend_n, EMIT_ACC_RESET, ws->acc, nullptr, ws->pend_identity, d_ri, static_cast<uint32_t*>(d_rx),
+                       resolve_stream(stream));
+}
+
+int splacu_vxm_masked(splacu_csr M, int dtype, int op_mult, int op_add, int op_select,
+                      uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
+                      uint32_t* d_ri, void* d_rx, uint32_t capacity, uint32_t* h_nr, splacu_workspace ws, void* stream) {
+    int rc = splacu_vxm_masked_begin(M, dtype, op_mult, op_add, op_select, nv, d_vi, d_vx, d_mask, ws, h_nr, stream);
+    if (rc) return rc;
+    if (*h_nr > capacity) {
+        // still drain the scratch so that the workspace stays usable: emit needs room, so report and reset by fill
+        Workspace* w = reinterpret_cast<Workspace*>(ws);
+        w->pending   = 0;
+        w->acc_clean = false;
+        cudaMemsetAsync(w->bitmap, 0, ((size_t) w->pend_n + 31) / 32 * 4, resolve_stream(stream));
+        set_error("splacu_vxm_masked: result has %u entries, capacity is %u", *h_nr, capacity);
+        return SPLACU_E_CAPACITY;
+    }
+    return splacu_vxm_masked_emit(ws, d_ri, d_rx, stream);
+}
+
+}// extern "C"

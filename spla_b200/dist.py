@@ -1,0 +1,87 @@
+"""Single-box multi-GPU sharding of the hot path: one process per GPU, torch.distributed (NCCL over NVLink 5 /
+NVSwitch on the GPU box, gloo in the CPU tests) as plumbing. Net-new relative to the reference, which is
+single-device.
+
+  mxv pull   rows are independent: contiguous row blocks chosen on the prefix sum of Ap so that every rank holds
+             ~nnz/P entries (nnz-balanced, not n-balanced). Each rank owns r[rows_p] and mask[rows_p]; a step is the
+             local masked mxv on the slice, written IN PLACE into the rank's window of a full-length vector, followed by
+             an all-gather of the windows -- the gathered vector is exactly the next step's input.
+  vxm push   column-sharded: rank p stores M[:, cols_p] as CSR over all rows (column ranges nnz-balanced), owns
+             mask[cols_p] and produces r[cols_p]; the windows are disjoint so the concatenation is already sorted.
+             The frontier exchange is an all-gather of the per-rank (count, indices, values).
+
+The partition helpers are pure index arithmetic on tensors and run on CPU tensors too (used by the gloo tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def balanced_boundaries(Ap, parts):
+    """Row boundaries b[0..parts] with b[0]=0, b[parts]=n such that each [b[p], b[p+1]) holds ~nnz/parts entries.
+    Ap: int64/int32 tensor [n+1] (any device)."""
+    n = Ap.numel() - 1
+    nnz = int(Ap[-1].item())
+    targets = torch.arange(1, parts, device=Ap.device, dtype=torch.int64) * nnz // parts
+    cuts = torch.searchsorted(Ap.to(torch.int64).contiguous(), targets, right=False).clamp(max=n)
+    b = [0] + [int(c) for c in cuts.tolist()] + [n]
+    for i in range(1, len(b)):  # keep it monotone when a huge row swallows several targets
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
+def row_slice(Ap, Aj, Ax, r0, r1):
+    """CSR slice of rows [r0, r1): (Ap_local int32 rebased to 0, Aj_local, Ax_local) -- all columns kept."""
+    k0, k1 = int(Ap[r0].item()), int(Ap[r1].item())
+    Ap_l = (Ap[r0:r1 + 1] - Ap[r0]).to(torch.int32).contiguous()
+    return Ap_l, Aj[k0:k1].contiguous(), Ax[k0:k1].contiguous()
+
+
+def column_slice(Ap, Aj, Ax, c0, c1):
+    """CSR over ALL rows restricted to columns [c0, c1), columns rebased to 0 (for column-sharded vxm)."""
+    n = Ap.numel() - 1
+    keep = (Aj >= c0) & (Aj < c1)
+    rows = torch.repeat_interleave(torch.arange(n, device=Ap.device), (Ap[1:] - Ap[:-1]).to(torch.int64))
+    cnt = torch.bincount(rows[keep], minlength=n)
+    Ap_l = torch.zeros(n + 1, dtype=torch.int64, device=Ap.device)
+    torch.cumsum(cnt, 0, out=Ap_l[1:])
+    return Ap_l.to(torch.int32), (Aj[keep] - c0).to(torch.int32).contiguous(), Ax[keep].contiguous()
+
+
+def column_boundaries(Aj, n_cols, parts):
+    """nnz-balanced column ranges for the column-sharded push."""
+    cnt = torch.bincount(Aj.to(torch.int64), minlength=n_cols)
+    Cp = torch.zeros(n_cols + 1, dtype=torch.int64, device=Aj.device)
+    torch.cumsum(cnt, 0, out=Cp[1:])
+    return balanced_boundaries(Cp, parts)
+
+
+def allgather_windows(full, bounds, group=None):
+    """In-place all-gather of the per-rank windows full[b[p]:b[p+1]] of one full-length vector.
+    Uneven windows: torch falls back to grouped broadcasts for NCCL, which on NVSwitch all run at full link rate."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return full
+    rank = dist.get_rank(group)
+    outs = [full[bounds[p]:bounds[p + 1]] for p in range(world)]
+    if full.dtype == torch.uint32:
+        outs = [o.view(torch.int32) for o in outs]
+    dist.all_gather(outs, outs[rank], group=group)
+    return full
+
+
+def exchange_frontier(vi_local, vx_local, offset, group=None):
+    """All-gather of sparse frontier pieces. Each rank contributes (indices local to its window + offset, values);
+    returns the concatenated global (vi, vx), sorted because windows are disjoint and ordered by rank."""
+    world = dist.get_world_size(group)
+    vi_g = vi_local + offset if offset else vi_local
+    if world == 1:
+        return vi_g, vx_local
+    cnt = torch.tensor([vi_local.numel()], dtype=torch.int64, device=vi_local.device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    sizes = [int(c.item()) for c in cnts]
+    vis = [torch.empty(s, dtype=vi_g.dtype, device=vi_g.device) for s in sizes]
+    vxs = [torch.empty(s, dtype=torch.int32, device=vi_g.device) for s in sizes]
+    dist.all_gather(vis, vi_g.contiguous(), group=group)
+    dist.all_gather(vxs, vx_local.contiguous().view(torch.int32), group=group)
+    return torch.cat(vis), torch.cat(vxs).view(vx_local.dtype)

@@ -1,0 +1,251 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/splacu.h), against
+ (1) the reference's known-answer vectors, (2) the committed outputs of the reference CPU backend
+ (tests/golden), (3) the plain-C oracle on seeded random inputs over every built-in op / type / select,
+ and (4) size-independent properties at full benchmark sizes.
+
+Bar: bit-exact for INT / UINT and every order-independent op; FLOAT PLUS / MULT reductions within 1e-5
+relative (north_star), the tolerance being written in gpu_util.assert_values.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import known_answers
+from cases import FLOAT, INT, UINT
+from gpu_util import assert_values, idx_dev, make_csr, to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def run_mxv(backend, dtype, om, oa, osel, n_cols, Ap, Aj, Ax, v, mask, init, ee):
+    M = make_csr(backend, len(Ap) - 1, n_cols, Ap, Aj, Ax)
+    r = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init, early_exit=ee)
+    backend.sync()
+    return to_np(r, cases.NP[dtype])
+
+
+def run_vxm(backend, dtype, om, oa, osel, n_cols, Ap, Aj, Ax, vi, vx, mask):
+    M = make_csr(backend, len(Ap) - 1, n_cols, Ap, Aj, Ax)
+    ri, rx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(mask, backend), om, oa, osel)
+    backend.sync()
+    return to_np(ri, np.uint32), to_np(rx, cases.NP[dtype])
+
+
+@pytest.mark.parametrize("case", known_answers.KNOWN, ids=[f'{c["kind"]}:{c["source"]}' for c in known_answers.KNOWN])
+def test_known_answers(backend, case):
+    Ap, Aj, Ax, dt = known_answers.as_arrays(case)
+    om, oa, osel = case["ops"]
+    mask = np.asarray(case["mask"], dtype=dt)
+    if case["kind"] == "mxv":
+        r = run_mxv(backend, case["dtype"], om, oa, osel, case["n_cols"], Ap, Aj, Ax, np.asarray(case["v"], dtype=dt), mask, case["init"], False)
+        np.testing.assert_array_equal(r, np.asarray(case["expect"], dtype=dt))
+    else:
+        ri, rx = run_vxm(backend, case["dtype"], om, oa, osel, case["n_cols"], Ap, Aj, Ax, np.asarray(case["vi"], dtype=np.uint32),
+                         np.asarray(case["vx"], dtype=dt), mask)
+        dense = np.zeros(case["n_cols"], dtype=dt)
+        dense[ri] = rx
+        np.testing.assert_array_equal(dense, np.asarray(case["expect"], dtype=dt))
+        assert np.all(np.diff(ri.astype(np.int64)) > 0)
+
+
+def test_golden_reference_outputs(backend):
+    """Against outputs of the unmodified reference CPU backend (tests/golden/mxv_vxm_reference.npz)."""
+    z = np.load(os.path.join(GOLDEN, "mxv_vxm_reference.npz"))
+    n = 0
+    for line in z["meta"]:
+        cid, dtype, om, oa, osel, n_rows, n_cols, ee = str(line).split(",")
+        dtype, n_cols, ee = int(dtype), int(n_cols), bool(int(ee))
+        p = f"c{cid}_"
+        exact = cases.exact_expected(dtype, om, oa) or ee
+        r = run_mxv(backend, dtype, om, oa, osel, n_cols, z[p + "Ap"], z[p + "Aj"], z[p + "Ax"], z[p + "v"], z[p + "mask_r"], z[p + "init"][0], ee)
+        assert_values(r, z[p + "r"], exact, what=f"mxv case {cid} {om}/{oa}/{osel} ee={ee}")
+        ri, rx = run_vxm(backend, dtype, om, oa, osel, n_cols, z[p + "Ap"], z[p + "Aj"], z[p + "Ax"], z[p + "vi"], z[p + "vx"], z[p + "mask_c"])
+        assert np.array_equal(ri, z[p + "ri"]), f"vxm pattern case {cid} {om}/{oa}/{osel}"
+        assert_values(rx, z[p + "rx"], cases.exact_expected(dtype, om, oa), what=f"vxm case {cid} {om}/{oa}/{osel}")
+        n += 1
+    assert n >= 100
+
+
+@pytest.mark.parametrize("dtype", [INT, UINT, FLOAT])
+def test_all_op_pairs_vs_oracle(backend, oracle, dtype):
+    """Every built-in (op_mult, op_add) pair, cycling selects and early_exit, skewed rows, non-identity init."""
+    rng = np.random.default_rng(1234 + dtype)
+    n_rows, n_cols = 301, 257
+    Ap, Aj, Ax = cases.rand_csr(rng, dtype, n_rows, n_cols, 5, skew=True)
+    M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+    k = 0
+    for om in cases.BIN_OPS:
+        for oa in cases.BIN_OPS:
+            if not (cases.op_valid(dtype, om) and cases.op_valid(dtype, oa)):
+                continue
+            if "DIV" in (om, oa) and dtype != FLOAT:
+                continue
+            osel = cases.SEL_OPS[k % 8]
+            ee = bool((k // 8) & 1)
+            k += 1
+            # FLOAT DIV: keep operands away from 0 so that no NaN is produced (NaN ordering under MIN/MAX is not part of the contract)
+            vk = "positive" if "DIV" in (om, oa) else "small"
+            v = cases.rand_values(rng, dtype, n_cols, vk)
+            mask = cases.rand_values(rng, dtype, n_rows)
+            init = cases.rand_values(rng, dtype, 1, vk)[0]
+            want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, ee)
+            got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init, early_exit=ee)
+            backend.sync()
+            assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa) or ee, what=f"mxv {om}/{oa}/{osel} ee={ee}")
+
+            vi, vx = cases.rand_frontier(rng, dtype, n_rows, 97, vk)
+            maskc = cases.rand_values(rng, dtype, n_cols)
+            wi, wx = oracle.vxm_masked(dtype, om, oa, osel, Ap, Aj, Ax, n_cols, vi, vx, maskc)
+            gi, gx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(maskc, backend), om, oa, osel)
+            backend.sync()
+            assert np.array_equal(to_np(gi, np.uint32), wi), f"vxm pattern {om}/{oa}/{osel}"
+            assert_values(to_np(gx, cases.NP[dtype]), wx, cases.exact_expected(dtype, om, oa), what=f"vxm {om}/{oa}/{osel}")
+    assert k > 100
+
+
+@pytest.mark.parametrize("dtype,om,oa,osel", cases.NAMED_SEMIRINGS)
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5000, 3000, 2), (4096, 4096, 40), (20000, 20000, 12)])
+def test_named_semirings_shapes(backend, oracle, dtype, om, oa, osel, shape):
+    """The semirings bfs / sssp / pr use, on ragged, rectangular and skewed shapes (rows > 2^13 nnz included)."""
+    n_rows, n_cols, avg = shape
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, om, oa, n_rows)).encode()))
+    kind = "positive" if (om, oa) == ("PLUS", "MIN") else ("unit" if dtype == FLOAT else "small")
+    Ap, Aj, Ax = cases.rand_csr(rng, dtype, n_rows, n_cols, avg, skew=n_rows > 100, kind=kind)
+    M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+    for ee in (False, True):
+        v = cases.rand_values(rng, dtype, n_cols, kind)
+        v[rng.random(n_cols) < 0.5] = 0
+        mask = cases.rand_values(rng, dtype, n_rows)
+        init = np.float32(3.0e38) if (om, oa) == ("PLUS", "MIN") else 0
+        want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, ee)
+        got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init, early_exit=ee)
+        backend.sync()
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa) or ee, what=f"mxv ee={ee}")
+    for nv in (0, 1, max(1, n_rows // 50), n_rows):
+        vi, vx = cases.rand_frontier(rng, dtype, n_rows, nv, kind)
+        maskc = cases.rand_values(rng, dtype, n_cols)
+        wi, wx = oracle.vxm_masked(dtype, om, oa, osel, Ap, Aj, Ax, n_cols, vi, vx, maskc)
+        gi, gx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(maskc, backend), om, oa, osel)
+        backend.sync()
+        assert np.array_equal(to_np(gi, np.uint32), wi), f"vxm pattern nv={nv}"
+        assert_values(to_np(gx, cases.NP[dtype]), wx, cases.exact_expected(dtype, om, oa), what=f"vxm nv={nv}")
+
+
+def test_edge_cases(backend, oracle):
+    # empty matrix: every r[i] = init (SURVEY 8a note B); empty frontier; NEVER; explicit zero frontier values (note F)
+    e = np.zeros(0, dtype=np.uint32)
+    Ap = np.zeros(6, dtype=np.uint32)
+    r = run_mxv(backend, INT, "MULT", "PLUS", "ALWAYS", 3, Ap, e, e.view(np.int32), np.ones(3, np.int32), np.ones(5, np.int32), 7, False)
+    np.testing.assert_array_equal(r, np.full(5, 7, np.int32))
+    Ap = np.array([0, 2, 3], dtype=np.uint32)
+    Aj = np.array([0, 1, 1], dtype=np.uint32)
+    Ax = np.array([0, 5, 7], dtype=np.int32)
+    z2 = np.zeros(2, np.int32)
+    ri, rx = run_vxm(backend, INT, "MULT", "PLUS", "ALWAYS", 2, Ap, Aj, Ax, e, e.view(np.int32), z2)
+    assert len(ri) == 0
+    ri, rx = run_vxm(backend, INT, "MULT", "PLUS", "NEVER", 2, Ap, Aj, Ax, np.array([0], np.uint32), np.array([1], np.int32), z2)
+    assert len(ri) == 0
+    ri, rx = run_vxm(backend, INT, "MULT", "PLUS", "ALWAYS", 2, Ap, Aj, Ax, np.array([0], np.uint32), np.array([0], np.int32), z2)
+    np.testing.assert_array_equal(ri, [0, 1])
+    np.testing.assert_array_equal(rx, [0, 0])
+    # early exit stops at the first position where the running sum != init (note E)
+    Ap = np.array([0, 3], dtype=np.uint32)
+    r = run_mxv(backend, INT, "MULT", "PLUS", "ALWAYS", 3, Ap, np.array([0, 1, 2], np.uint32), np.array([1, 1, 1], np.int32),
+                np.array([0, 3, 4], np.int32), np.zeros(1, np.int32), 0, True)
+    assert r[0] == 3
+    # argument order of op_mult (note A): mxv mult(a, v), vxm mult(v, a)
+    Ap = np.array([0, 1], dtype=np.uint32)
+    r = run_mxv(backend, INT, "MINUS", "PLUS", "ALWAYS", 1, Ap, np.array([0], np.uint32), np.array([10], np.int32), np.array([3], np.int32),
+                np.zeros(1, np.int32), 0, False)
+    assert r[0] == 7
+    ri, rx = run_vxm(backend, INT, "MINUS", "PLUS", "ALWAYS", 1, Ap, np.array([0], np.uint32), np.array([10], np.int32), np.array([0], np.uint32),
+                     np.array([3], np.int32), np.zeros(1, np.int32))
+    assert rx[0] == -7
+
+
+def test_repeated_vxm_reuses_clean_scratch(backend, oracle):
+    """The dense accumulator / bitmap scratch is reset by emit: alternating semirings must not leak state."""
+    rng = np.random.default_rng(77)
+    n = 5000
+    Ap, Aj, Ax = cases.rand_csr(rng, INT, n, n, 8, skew=True)
+    M = make_csr(backend, n, n, Ap, Aj, Ax)
+    for it in range(6):
+        om, oa = [("MULT", "PLUS"), ("BAND", "BOR"), ("PLUS", "MIN"), ("MULT", "MAX"), ("FIRST", "SECOND"), ("MULT", "LOR")][it]
+        vi, vx = cases.rand_frontier(rng, INT, n, 300 + 100 * it)
+        mask = cases.rand_values(rng, INT, n)
+        wi, wx = oracle.vxm_masked(INT, om, oa, "EQZERO", Ap, Aj, Ax, n, vi, vx, mask)
+        gi, gx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(mask, backend), om, oa, "EQZERO")
+        backend.sync()
+        assert np.array_equal(to_np(gi, np.uint32), wi) and np.array_equal(to_np(gx, np.int32), wx), (it, om, oa)
+
+
+def test_format_glue(backend):
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 32, 33, 1000, 100003):
+        dense = cases.rand_values(rng, FLOAT, n)
+        dense[rng.random(n) < 0.6] = 7.5
+        ri, rx = backend.dense_to_coo(to_dev(dense, backend), 7.5)
+        backend.sync()
+        keep = np.nonzero(dense != np.float32(7.5))[0]
+        np.testing.assert_array_equal(to_np(ri, np.uint32), keep.astype(np.uint32))
+        np.testing.assert_array_equal(to_np(rx, np.float32), dense[keep])
+        back = backend.coo_to_dense(n, 7.5, ri, rx)
+        backend.sync()
+        np.testing.assert_array_equal(to_np(back, np.float32), dense)
+
+
+def test_properties_at_scale(backend):
+    """Size-independent checks at a benchmark-like size (RMAT scale 20, ~30 M nnz) where the CPU oracle is too slow:
+    linearity of MULT/PLUS, mxv <-> vxm duality on a symmetric matrix, mask monotonicity, idempotence of BOR."""
+    from spla_b200 import graphs
+
+    n, Ap64, Aj = graphs.rmat(20, seed=5, device=backend.device)
+    torch.cuda.synchronize()
+    nnz = Aj.numel()
+    Ap = Ap64.to(torch.int32)
+    ones_i = torch.ones(nnz, dtype=torch.int32, device=backend.device)
+    Mi = backend.csr(n, n, Ap, Aj, ones_i)
+    g = torch.Generator(device=backend.device)
+    g.manual_seed(11)
+    x = torch.randint(0, 5, (n,), generator=g, device=backend.device, dtype=torch.int32)
+    y = torch.randint(0, 5, (n,), generator=g, device=backend.device, dtype=torch.int32)
+    zeros = torch.zeros(n, dtype=torch.int32, device=backend.device)
+    torch.cuda.synchronize()  # inputs were produced on torch's default stream; the backend runs on its own stream
+    with torch.cuda.stream(backend.stream):
+        rx_ = backend.mxv_masked(Mi, x, zeros, "MULT", "PLUS", "EQZERO", 0)
+        ry_ = backend.mxv_masked(Mi, y, zeros, "MULT", "PLUS", "EQZERO", 0)
+        rxy = backend.mxv_masked(Mi, x + y, zeros, "MULT", "PLUS", "EQZERO", 0)
+        backend.sync()
+        assert torch.equal(rxy, rx_ + ry_)  # linearity, exact in int32
+        deg = (Ap64[1:] - Ap64[:-1]).to(torch.int32)
+        rdeg = backend.mxv_masked(Mi, torch.ones_like(x), zeros, "MULT", "PLUS", "EQZERO", 0)
+        backend.sync()
+        assert torch.equal(rdeg, deg)  # A * 1 = row degrees
+        # duality on the symmetric matrix: (f x A)[j] == (A x f)[j] for a sparse f (reference bfs relies on it)
+        vi = torch.nonzero(x == 4).flatten().to(torch.int32)
+        vx = torch.full((vi.numel(),), 3, dtype=torch.int32, device=backend.device)
+        f_dense = backend.coo_to_dense(n, 0, vi, vx)
+        pull = backend.mxv_masked(Mi, f_dense, zeros, "MULT", "PLUS", "EQZERO", 0)
+        ri, rxv = backend.vxm_masked(Mi, vi, vx, zeros, "MULT", "PLUS", "EQZERO")
+        backend.sync()
+        push_dense = backend.coo_to_dense(n, 0, ri, rxv)
+        backend.sync()
+        assert torch.equal(push_dense, pull)
+        assert bool((ri[1:] > ri[:-1]).all())  # sortedness
+        # mask monotonicity: masked result == unmasked result where selected, init elsewhere
+        mask = (y > 2).to(torch.int32)
+        rm = backend.mxv_masked(Mi, x, mask, "MULT", "PLUS", "EQZERO", -1)
+        backend.sync()
+        assert torch.equal(rm, torch.where((mask == 0) & (deg > 0), rx_ - 1, torch.full_like(rx_, -1)))
+        # BFS semiring: early-exit result equals the full OR-reduction (values 0/1), and is idempotent
+        fb = (x == 4).to(torch.int32)
+        full = backend.mxv_masked(Mi, fb, zeros, "BAND", "BOR", "EQZERO", 0)
+        ee = backend.mxv_masked(Mi, fb, zeros, "BAND", "BOR", "EQZERO", 0, early_exit=True)
+        backend.sync()
+        assert torch.equal(full, ee)
+        assert torch.equal(full, (pull > 0).to(torch.int32))
