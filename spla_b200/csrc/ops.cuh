@@ -195,12 +195,13 @@ namespace splacu {
                 case SPLACU_PLUS: atomicAdd(a, val); return;
                 case SPLACU_MIN:
                     if (!(val < cur)) return;// idempotent: skip when no change (stale read only costs an atomic)
-                    if (val >= 0.0f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(val));
+                    // ordered-int trick, keyed on the SIGN BIT (so that -0.0 takes the negative branch)
+                    if (__float_as_int(val) >= 0) atomicMin(reinterpret_cast<int*>(a), __float_as_int(val));
                     else atomicMax(reinterpret_cast<unsigned int*>(a), __float_as_uint(val));
                     return;
                 case SPLACU_MAX:
                     if (!(cur < val)) return;
-                    if (val >= 0.0f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(val));
+                    if (__float_as_int(val) >= 0) atomicMax(reinterpret_cast<int*>(a), __float_as_int(val));
                     else atomicMin(reinterpret_cast<unsigned int*>(a), __float_as_uint(val));
                     return;
                 case SPLACU_LOR:

@@ -1,0 +1,72 @@
+// cuda_accelerator.hpp -- spla Accelerator implementation for one CUDA device (B200, sm_100a).
+//
+// Plugs into the reference's backend interface (reference src/core/accelerator.hpp:58-69) next to
+// CLAccelerator (reference src/opencl/cl_accelerator.hpp:62-136). It owns nothing but a handle to the
+// splacu C-ABI runtime (include/splacu.h): host C++ never sees a CUDA header.
+#ifndef SPLA_CUDA_ACCELERATOR_HPP
+#define SPLA_CUDA_ACCELERATOR_HPP
+
+#include <core/accelerator.hpp>
+#include <core/logger.hpp>
+#include <spla/library.hpp>
+
+#include <splacu.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace spla {
+
+#define GPU_CUDA_SUFFIX                      "__cuda"
+#define MAKE_KEY_CUDA_0(name, type)          MAKE_KEY_0(name, type) + GPU_CUDA_SUFFIX
+#define MAKE_KEY_CUDA_1(name, op)            MAKE_KEY_1(name, op) + GPU_CUDA_SUFFIX
+#define MAKE_KEY_CUDA_2(name, op1, op2)      MAKE_KEY_2(name, op1, op2) + GPU_CUDA_SUFFIX
+#define MAKE_KEY_CUDA_3(name, op1, op2, op3) MAKE_KEY_3(name, op1, op2, op3) + GPU_CUDA_SUFFIX
+
+// every splacu call site: a failing device call becomes a C++ exception, which the dispatcher turns into
+// Status::Error (reference src/core/dispatcher.cpp:62-80). There is no CPU fallback on this path.
+#define SPLACU_CALL(expr)                                                                                    \
+    do {                                                                                                     \
+        int _rc = (expr);                                                                                    \
+        if (_rc != 0) throw std::runtime_error(std::string("cuda backend: " #expr " failed: ") + splacu_last_error()); \
+    } while (0)
+
+    /**
+     * @class CudaAccelerator
+     * @brief Single-device CUDA acceleration backend
+     */
+    class CudaAccelerator final : public Accelerator {
+    public:
+        ~CudaAccelerator() override;
+
+        Status             init() override;
+        Status             set_platform(int index) override;
+        Status             set_device(int index) override;
+        Status             set_queues_count(int count) override;
+        const std::string& get_name() override;
+        const std::string& get_description() override;
+        const std::string& get_suffix() override;
+
+        /** scratch shared by vxm / compaction / reductions; one in-order stream => one workspace */
+        splacu_workspace get_workspace() { return m_workspace; }
+        /** the backend's in-order stream (NULL selects it on the C-ABI side) */
+        void* get_stream() { return nullptr; }
+
+    private:
+        std::string      m_name        = "CUDA";
+        std::string      m_description = "no device";
+        std::string      m_suffix      = GPU_CUDA_SUFFIX;
+        splacu_workspace m_workspace   = nullptr;
+        int              m_device      = 0;
+    };
+
+    /** @return the active CUDA accelerator; throws when another (or no) accelerator is installed */
+    static inline CudaAccelerator* get_acc_cuda() {
+        auto* acc = dynamic_cast<CudaAccelerator*>(Library::get()->get_accelerator());
+        if (!acc) throw std::runtime_error("cuda backend: CudaAccelerator is not the active accelerator");
+        return acc;
+    }
+
+}// namespace spla
+
+#endif//SPLA_CUDA_ACCELERATOR_HPP
