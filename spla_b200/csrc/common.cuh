@@ -63,12 +63,16 @@ namespace splacu {
         const uint32_t* Ap = nullptr;
         const uint32_t* Aj = nullptr;
         const uint32_t* Ax = nullptr;
-        // load-balancing metadata for the streaming pull kernel (mxv_pull.cu), owned
+        // load-balancing metadata for the streaming pull kernel (mxv_pull.cu), owned by the handle
+        uint32_t  tile         = 0;      // entries per nnz tile (kMxvTile)
         uint32_t  n_tiles      = 0;
-        uint32_t* tile_row     = nullptr;// [n_tiles+1] first row touching each nnz tile
-        uint32_t  max_row_nnz  = 0;
+        uint32_t* tile_row     = nullptr;// [n_tiles+1] first row that STARTS in each nnz tile
+        uint32_t* carry        = nullptr;// [2*n_tiles] (head, tail) partials of rows crossing tile borders
+        bool      vec_ok       = false;  // Aj / Ax 16-byte aligned: 128-bit streaming loads
         float     avg_row_nnz  = 0.f;
     };
+
+    static constexpr int kMxvTile = 4096;// nnz per tile of the streaming pull kernel
 
     // ---- workspace ------------------------------------------------------------------------
     struct Workspace {

@@ -261,6 +261,8 @@ int splacu_csr_destroy(splacu_csr handle) {
     if (!handle) return SPLACU_OK;
     Csr* M = reinterpret_cast<Csr*>(handle);
     if (M->tile_row) cudaFree(M->tile_row);
+    if (M->carry) cudaFree(M->carry);
+    cudaGetLastError();
     delete M;
     return SPLACU_OK;
 }

@@ -33,7 +33,8 @@ def row_slice(Ap, Aj, Ax, r0, r1):
     """CSR slice of rows [r0, r1): (Ap_local int32 rebased to 0, Aj_local, Ax_local) -- all columns kept."""
     k0, k1 = int(Ap[r0].item()), int(Ap[r1].item())
     Ap_l = (Ap[r0:r1 + 1] - Ap[r0]).to(torch.int32).contiguous()
-    return Ap_l, Aj[k0:k1].contiguous(), Ax[k0:k1].contiguous()
+    # clone: fresh allocations are 16-byte aligned, which the 128-bit streaming loads of the pull kernel need
+    return Ap_l, Aj[k0:k1].clone(), Ax[k0:k1].clone()
 
 
 def column_slice(Ap, Aj, Ax, c0, c1):
