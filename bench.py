@@ -241,6 +241,7 @@ def main():
     mask_l = torch.ones(r1 - r0, dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
     M = be.csr(r1 - r0, n, Ap_l, Aj_l, Ax_l)
+    csr_info = be.csr_info(M)
 
     def step(src, dst):
         be.mxv_masked(M, src, mask_l, *OPS, 0.0, out=dst[r0:r1])
@@ -340,14 +341,15 @@ def main():
         line = {
             "metric": METRIC, "value": gteps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, n, nnz, world),
+            "config": dict(workload_config(args, n, nnz, world), kernel=f"mxv_wtile_kernel, {csr_info['n_tiles']} warp tiles of 512 nnz, "
+                                                                          f"{csr_info['n_hub']} hub columns"),
             "clocks": clocks,
             "e2e": {"value": nnz / t_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,
                     "steps": e2e_steps, "result_checksum": checksum,
                     "path": "splacu_memcpy_h2d(v, mask) -> splacu_mxv_masked -> splacu_memcpy_d2h(r) -> splacu_sync, pinned host buffers"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "mxv_rows_kernel", "achieved": achieved_min, "peak": peak, "unit": "GB/s", "frac": achieved_min / peak,
-                         "traffic": ncu_traffic("mxv_rows_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "roofline": {"bound": "hbm", "kernel": "mxv_wtile_kernel", "achieved": achieved_min, "peak": peak, "unit": "GB/s", "frac": achieved_min / peak,
+                         "traffic": ncu_traffic("mxv_wtile_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": ms_kernel, "note": "rank-0 bytes, slowest rank's bandwidth" if world > 1 else "one launch = one step"},
             "cpu_baseline": cpu,
         }

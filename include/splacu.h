@@ -68,6 +68,11 @@ SPLACU_API void*       splacu_default_stream(void);          /* the backend's ow
 SPLACU_API int         splacu_sync(void* stream);            /* cudaStreamSynchronize */
 SPLACU_API const char* splacu_last_error(void);
 SPLACU_API int         splacu_launch_count(uint64_t* count); /* kernels launched by this library so far */
+/* tuning knobs, read when a matrix handle is created (the reference's counterpart are the vendor heuristics of
+ * src/opencl/cl_accelerator.cpp:84-175): "mxv_hub" 0 = off, 1 = auto (default), 2 = always build the hub cache of
+ * the pull kernel; "mxv_hub_min_count" = references a column needs to earn a hub slot (default 16) */
+SPLACU_API int         splacu_set_option(const char* name, int64_t value);
+SPLACU_API int         splacu_get_option(const char* name, int64_t* value);
 
 /* device memory: replaces cl::Buffer creation / enqueueRead / enqueueWrite in
  * reference src/opencl/cl_format_dense_vec.hpp:43-87, cl_format_coo_vec.hpp:43-125, cl_format_csr.hpp:40-96 */
@@ -90,6 +95,8 @@ typedef struct splacu_csr_t* splacu_csr;
 SPLACU_API int splacu_csr_create(splacu_csr* M, uint32_t n_rows, uint32_t n_cols, uint32_t nnz,
                                  const uint32_t* d_Ap, const uint32_t* d_Aj, const void* d_Ax, void* stream);
 SPLACU_API int splacu_csr_destroy(splacu_csr M);
+/* introspection for tests / logs: nnz tiles of the pull kernel and hub-cache slots (either pointer may be NULL) */
+SPLACU_API int splacu_csr_info(splacu_csr M, uint32_t* n_tiles, uint32_t* n_hub);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 

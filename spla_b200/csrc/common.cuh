@@ -66,13 +66,23 @@ namespace splacu {
         // load-balancing metadata for the streaming pull kernel (mxv_pull.cu), owned by the handle
         uint32_t  tile         = 0;      // entries per nnz tile (kMxvTile)
         uint32_t  n_tiles      = 0;
-        uint32_t* tile_row     = nullptr;// [n_tiles+1] first row that STARTS in each nnz tile
+        uint2*    tile_rows    = nullptr;// [n_tiles] (first row with entries in the tile, one past the last row starting in it)
         uint32_t* carry        = nullptr;// [2*n_tiles] (head, tail) partials of rows crossing tile borders
         bool      vec_ok       = false;  // Aj / Ax 16-byte aligned: 128-bit streaming loads
         float     avg_row_nnz  = 0.f;
+        // hub cache of the pull kernel: the n_hub most referenced columns live in shared memory
+        uint32_t  n_hub        = 0;
+        uint32_t  n_hub_smem   = 0;      // slots [0, n_hub_smem) are staged in shared memory, the rest is served by L1
+        uint32_t* hub_cols     = nullptr;// [n_hub] column ids, most referenced first
+        uint32_t* hub_vals     = nullptr;// [n_hub] v[hub_cols[s]], packed per call
+        uint32_t* Aj_hub       = nullptr;// [nnz] Aj with hub columns replaced by (0x80000000 | slot)
     };
 
-    static constexpr int kMxvTile = 4096;// nnz per tile of the streaming pull kernel
+    static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
+
+    // ---- tuning options (splacu_set_option) -------------------------------------------------
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_COUNT };
+    int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------
     struct Workspace {

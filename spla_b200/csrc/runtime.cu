@@ -31,6 +31,10 @@ namespace splacu {
         return (int) e;
     }
 
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto, 2 force*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem"};
+    int64_t get_option(int opt) { return g_options[opt]; }
+
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
 
     cudaStream_t resolve_stream(void* stream) { return stream ? (cudaStream_t) stream : g_stream; }
@@ -178,6 +182,36 @@ int splacu_launch_count(uint64_t* count) {
     return SPLACU_OK;
 }
 
+int splacu_set_option(const char* name, int64_t value) {
+    SPLACU_REQUIRE(name, "null option name");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, g_option_names[i]) == 0) {
+            g_options[i] = value;
+            return SPLACU_OK;
+        }
+    set_error("splacu_set_option: unknown option '%s'", name);
+    return SPLACU_E_INVALID;
+}
+
+int splacu_get_option(const char* name, int64_t* value) {
+    SPLACU_REQUIRE(name && value, "null pointer");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, g_option_names[i]) == 0) {
+            *value = g_options[i];
+            return SPLACU_OK;
+        }
+    set_error("splacu_get_option: unknown option '%s'", name);
+    return SPLACU_E_INVALID;
+}
+
+int splacu_csr_info(splacu_csr handle, uint32_t* n_tiles, uint32_t* n_hub) {
+    SPLACU_REQUIRE(handle, "null matrix handle");
+    const Csr* M = reinterpret_cast<const Csr*>(handle);
+    if (n_tiles) *n_tiles = M->n_tiles;
+    if (n_hub) *n_hub = M->n_hub;
+    return SPLACU_OK;
+}
+
 int splacu_malloc(void** d_ptr, size_t bytes) {
     SPLACU_CHECK_INIT();
     SPLACU_REQUIRE(d_ptr, "null pointer");
@@ -260,8 +294,11 @@ int splacu_csr_create(splacu_csr* out, uint32_t n_rows, uint32_t n_cols, uint32_
 int splacu_csr_destroy(splacu_csr handle) {
     if (!handle) return SPLACU_OK;
     Csr* M = reinterpret_cast<Csr*>(handle);
-    if (M->tile_row) cudaFree(M->tile_row);
+    if (M->tile_rows) cudaFree(M->tile_rows);
     if (M->carry) cudaFree(M->carry);
+    if (M->hub_cols) cudaFree(M->hub_cols);
+    if (M->hub_vals) cudaFree(M->hub_vals);
+    if (M->Aj_hub) cudaFree(M->Aj_hub);
     cudaGetLastError();
     delete M;
     return SPLACU_OK;

@@ -136,6 +136,48 @@ def test_named_semirings_shapes(backend, oracle, dtype, om, oa, osel, shape):
         assert_values(to_np(gx, cases.NP[dtype]), wx, cases.exact_expected(dtype, om, oa), what=f"vxm nv={nv}")
 
 
+@pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "MULT", "PLUS", "EQZERO"), (UINT, "BAND", "BOR", "ALWAYS"), (FLOAT, "MULT", "PLUS", "ALWAYS"),
+                                               (FLOAT, "PLUS", "MIN", "NQZERO"), (INT, "LAND", "LOR", "GTZERO")])
+@pytest.mark.parametrize("hub_smem,hub_total", [(0, 64), (16, 64), (256, 256), (128, 4096)])
+def test_pull_hub_cache_forced(backend, oracle, dtype, om, oa, osel, hub_smem, hub_total):
+    """The hub-cache variant of the streaming pull kernel (most referenced columns served from shared memory / the packed
+    hub table) is normally reserved for large matrices; force it on small skewed ones and compare with the oracle."""
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, om, oa, hub_smem, hub_total)).encode()))
+    n_rows, n_cols = 3000, 2500
+    kind = "positive" if (om, oa) == ("PLUS", "MIN") else ("unit" if dtype == FLOAT else "small")
+    Ap, Aj, Ax = cases.rand_csr(rng, dtype, n_rows, n_cols, 30, skew=True, kind=kind)
+    # make the column popularity skewed as well: fold most columns onto a few hubs, keep rows sorted + duplicate free
+    hubs = rng.integers(0, n_cols, 40, dtype=np.int64)
+    fold = rng.random(len(Aj)) < 0.6
+    Aj = Aj.astype(np.int64)
+    Aj[fold] = hubs[rng.integers(0, len(hubs), int(fold.sum()))]
+    rows = np.repeat(np.arange(n_rows, dtype=np.int64), np.diff(Ap.astype(np.int64)))
+    key, first = np.unique(rows * n_cols + Aj, return_index=True)
+    Aj, Ax, rows = (key % n_cols).astype(np.uint32), Ax[first], key // n_cols
+    Ap = np.zeros(n_rows + 1, dtype=np.uint32)
+    Ap[1:] = np.cumsum(np.bincount(rows, minlength=n_rows))
+    try:
+        backend.set_option("mxv_hub", 2)
+        backend.set_option("mxv_hub_smem", hub_smem)
+        backend.set_option("mxv_hub_total", hub_total)
+        backend.set_option("mxv_hub_min_count", 2)
+        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+        assert backend.csr_info(M)["n_hub"] > 0
+    finally:
+        backend.set_option("mxv_hub", 1)
+        backend.set_option("mxv_hub_smem", 16384)
+        backend.set_option("mxv_hub_total", 1 << 20)
+        backend.set_option("mxv_hub_min_count", 16)
+    for rep in range(2):
+        v = cases.rand_values(rng, dtype, n_cols, kind)
+        mask = cases.rand_values(rng, dtype, n_rows)
+        init = np.float32(3.0e38) if (om, oa) == ("PLUS", "MIN") else 0
+        want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
+        got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
+        backend.sync()
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"hub mxv rep {rep}")
+
+
 def test_edge_cases(backend, oracle):
     # empty matrix: every r[i] = init (SURVEY 8a note B); empty frontier; NEVER; explicit zero frontier values (note F)
     e = np.zeros(0, dtype=np.uint32)

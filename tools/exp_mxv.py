@@ -48,10 +48,23 @@ def report(name, ms):
 
 with torch.cuda.stream(be.stream):
     r = torch.empty(n, device=dev)
+    be.set_option("mxv_hub", 0)
     M = be.csr(n, n, Ap32, Aj, Ax)
     report("orig ALWAYS", timeit(lambda: be.mxv_masked(M, v, None, "MULT", "PLUS", "ALWAYS", 0.0, out=r)))
     report("orig NQZERO all-ones mask", timeit(lambda: be.mxv_masked(M, v, mask, "MULT", "PLUS", "NQZERO", 0.0, out=r)))
     r0 = r.clone()
+    for smem_e, total, na in ((8192, 1048576, 0), (12288, 1048576, 0), (16384, 1048576, 0), (20480, 1048576, 0)):
+        be.set_option("mxv_hub", 2)
+        be.set_option("mxv_hub_total", total)
+        be.set_option("mxv_hub_smem", smem_e)
+        Mh = be.csr(n, n, Ap32, Aj, Ax)
+        report(f"hub smem {smem_e} total {total} na {na}", timeit(lambda: be.mxv_masked(Mh, v, None, "MULT", "PLUS", "ALWAYS", 0.0, out=r)))
+        be.sync()
+        print("   max rel diff hub vs plain:", ((r - r0).abs() / r0.abs().clamp(min=1e-30)).max().item())
+        report(f"   same, NQZERO all-ones mask", timeit(lambda: be.mxv_masked(Mh, v, mask, "MULT", "PLUS", "NQZERO", 0.0, out=r)))
+        del Mh
+    be.set_option("mxv_hub", 1)
+    be.set_option("mxv_hub_smem", 16384)
     # relabel columns by descending degree: new id = rank
     order = torch.argsort(deg, descending=True, stable=True)
     rank = torch.empty_like(order)
@@ -69,6 +82,6 @@ with torch.cuda.stream(be.stream):
         m = (torch.rand(n, device=dev) < dens).float()
         sel = int(deg[m != 0].sum().item())
         torch.cuda.synchronize()
-        ms = timeit(lambda: be.mxv_masked(M, v, m, "MULT", "PLUS", "NQZERO", 0.0, out=r))
+        ms = timeit(lambda: be.mxv_masked(M2, v2, m, "MULT", "PLUS", "NQZERO", 0.0, out=r))
         alg = 4 * (n + 1) + 8 * n + 8 * sel + 4 * min(n, sel)
-        print(f"mask density {dens}: {ms:.3f} ms  {sel / ms / 1e6:.1f} GTEPS(selected)  {alg / ms / 1e6:.1f} GB/s alg", flush=True)
+        print(f"mask density {dens} (hub + relabel): {ms:.3f} ms  {sel / ms / 1e6:.1f} GTEPS(selected)  {alg / ms / 1e6:.1f} GB/s alg", flush=True)
