@@ -81,7 +81,7 @@ namespace splacu {
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------

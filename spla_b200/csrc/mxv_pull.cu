@@ -30,6 +30,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstring>
+
 namespace splacu {
 
     static constexpr int      kBlock     = 256;
@@ -491,9 +493,44 @@ namespace splacu {
         return 0;
     }
 
+    // keep v resident in L2 while the CSR arrays stream through it (access-policy window on the launching stream)
+    static int set_persisting_window(const void* base, size_t bytes, cudaStream_t s) {
+        static const void*  cur_base  = nullptr;
+        static size_t       cur_bytes = 0;
+        static cudaStream_t cur_s     = nullptr;
+        static size_t       max_win = 0, max_persist = 0;
+        static bool         probed = false;
+        if (!probed) {
+            probed = true;
+            int dev = 0, v1 = 0, v2 = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&v1, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            cudaDeviceGetAttribute(&v2, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            max_win     = (size_t) v1;
+            max_persist = (size_t) v2;
+            if (max_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, max_persist);
+            cudaGetLastError();
+        }
+        if (!max_win || !max_persist) return 0;
+        if (bytes > max_win) bytes = max_win;
+        if (base == cur_base && bytes == cur_bytes && s == cur_s) return 0;
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr  = const_cast<void*>(base);
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio  = bytes <= max_persist ? 1.0f : (float) max_persist / (float) bytes;
+        attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+        SPLACU_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+        cur_base = base, cur_bytes = bytes, cur_s = s;
+        return 0;
+    }
+
     template<typename T, typename S>
     static int launch_tiles(S sr, Select sel, const Csr* M, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
         int rc;
+        if (get_option(OPT_MXV_L2_PERSIST) && (size_t) M->nnz * 8 > (size_t) 64 << 20)
+            if ((rc = set_persisting_window(v, (size_t) M->n_cols * 4, s))) return rc;
         if (M->n_hub) {
             mxv_hub_pack_kernel<<<(M->n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->hub_cols, M->n_hub, reinterpret_cast<const uint32_t*>(v), M->hub_vals);
             SPLACU_LAUNCH_CHECK();

@@ -31,8 +31,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto, 2 force*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto, 2 force*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }

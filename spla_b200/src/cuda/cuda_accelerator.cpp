@@ -1,5 +1,7 @@
 #include "cuda_accelerator.hpp"
 
+#include <cuda/cuda_storage.hpp>
+
 namespace spla {
 
     CudaAccelerator::~CudaAccelerator() {
@@ -16,6 +18,8 @@ namespace spla {
             LOG_MSG(Status::DeviceNotFound, "no cuda device found");
             return Status::DeviceNotFound;
         }
+        // device formats: constructors / validators / converters in the Acc* slots of the storage managers
+        register_formats_cuda();
         return set_device(0);
     }
 

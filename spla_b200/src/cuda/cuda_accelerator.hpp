@@ -17,6 +17,11 @@
 
 namespace spla {
 
+    /** Value a maintainer adds to `enum class AcceleratorType` (reference include/spla/config.hpp:89-94) as `Cuda = 2`,
+     *  mirrored in the C API as SPLA_ACCELERATOR_TYPE_CUDA (reference include/spla.h:83-86). Kept here so that the
+     *  public headers of the reference compile unmodified. */
+    constexpr AcceleratorType ACCELERATOR_TYPE_CUDA = static_cast<AcceleratorType>(2);
+
 #define GPU_CUDA_SUFFIX                      "__cuda"
 #define MAKE_KEY_CUDA_0(name, type)          MAKE_KEY_0(name, type) + GPU_CUDA_SUFFIX
 #define MAKE_KEY_CUDA_1(name, op)            MAKE_KEY_1(name, op) + GPU_CUDA_SUFFIX

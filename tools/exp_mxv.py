@@ -53,16 +53,14 @@ with torch.cuda.stream(be.stream):
     report("orig ALWAYS", timeit(lambda: be.mxv_masked(M, v, None, "MULT", "PLUS", "ALWAYS", 0.0, out=r)))
     report("orig NQZERO all-ones mask", timeit(lambda: be.mxv_masked(M, v, mask, "MULT", "PLUS", "NQZERO", 0.0, out=r)))
     r0 = r.clone()
-    for smem_e, total, na in ((8192, 1048576, 0), (12288, 1048576, 0), (16384, 1048576, 0), (20480, 1048576, 0)):
-        be.set_option("mxv_hub", 2)
-        be.set_option("mxv_hub_total", total)
-        be.set_option("mxv_hub_smem", smem_e)
-        Mh = be.csr(n, n, Ap32, Aj, Ax)
-        report(f"hub smem {smem_e} total {total} na {na}", timeit(lambda: be.mxv_masked(Mh, v, None, "MULT", "PLUS", "ALWAYS", 0.0, out=r)))
-        be.sync()
-        print("   max rel diff hub vs plain:", ((r - r0).abs() / r0.abs().clamp(min=1e-30)).max().item())
-        report(f"   same, NQZERO all-ones mask", timeit(lambda: be.mxv_masked(Mh, v, mask, "MULT", "PLUS", "NQZERO", 0.0, out=r)))
-        del Mh
+    be.set_option("mxv_hub", 1)
+    Mh = be.csr(n, n, Ap32, Aj, Ax)
+    for persist in (0, 1, 0, 1):
+        be.set_option("mxv_l2_persist", persist)
+        report(f"hub default, l2 persist {persist} ALWAYS", timeit(lambda: be.mxv_masked(Mh, v, None, "MULT", "PLUS", "ALWAYS", 0.0, out=r)))
+        report(f"hub default, l2 persist {persist} NQZERO", timeit(lambda: be.mxv_masked(Mh, v, mask, "MULT", "PLUS", "NQZERO", 0.0, out=r)))
+    be.set_option("mxv_l2_persist", 0)
+    del Mh
     be.set_option("mxv_hub", 1)
     be.set_option("mxv_hub_smem", 16384)
     # relabel columns by descending degree: new id = rank
