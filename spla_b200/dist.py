@@ -58,31 +58,47 @@ def column_boundaries(Aj, n_cols, parts):
 
 def allgather_windows(full, bounds, group=None):
     """In-place all-gather of the per-rank windows full[b[p]:b[p+1]] of one full-length vector.
-    Uneven windows: torch falls back to grouped broadcasts for NCCL, which on NVSwitch all run at full link rate."""
+    The windows are nnz-balanced, hence uneven: equal windows take one all_gather_into_tensor, uneven ones one broadcast per
+    owner straight into place (no staging copy; issued together, on NVSwitch every broadcast runs at full link rate)."""
     world = dist.get_world_size(group)
     if world == 1:
         return full
-    rank = dist.get_rank(group)
-    outs = [full[bounds[p]:bounds[p + 1]] for p in range(world)]
-    if full.dtype == torch.uint32:
-        outs = [o.view(torch.int32) for o in outs]
-    dist.all_gather(outs, outs[rank], group=group)
+    buf = full.view(torch.int32) if full.dtype == torch.uint32 else full
+    sizes = [bounds[p + 1] - bounds[p] for p in range(world)]
+    if len(set(sizes)) == 1 and sizes[0] > 0:
+        rank = dist.get_rank(group)
+        dist.all_gather_into_tensor(buf[bounds[0]:bounds[world]], buf[bounds[rank]:bounds[rank + 1]].clone(), group=group)
+        return full
+    works = []
+    for p in range(world):
+        if sizes[p] > 0:
+            src = dist.get_global_rank(group, p) if group is not None else p
+            works.append(dist.broadcast(buf[bounds[p]:bounds[p + 1]], src=src, group=group, async_op=True))
+    for w in works:
+        w.wait()
     return full
 
 
 def exchange_frontier(vi_local, vx_local, offset, group=None):
     """All-gather of sparse frontier pieces. Each rank contributes (indices local to its window + offset, values);
-    returns the concatenated global (vi, vx), sorted because windows are disjoint and ordered by rank."""
+    returns the concatenated global (vi, vx), sorted because windows are disjoint and ordered by rank.
+    Pieces are uneven: counts are exchanged first, then the pieces travel padded to the largest one."""
     world = dist.get_world_size(group)
     vi_g = vi_local + offset if offset else vi_local
     if world == 1:
         return vi_g, vx_local
-    cnt = torch.tensor([vi_local.numel()], dtype=torch.int64, device=vi_local.device)
-    cnts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(cnts, cnt, group=group)
-    sizes = [int(c.item()) for c in cnts]
-    vis = [torch.empty(s, dtype=vi_g.dtype, device=vi_g.device) for s in sizes]
-    vxs = [torch.empty(s, dtype=torch.int32, device=vi_g.device) for s in sizes]
-    dist.all_gather(vis, vi_g.contiguous(), group=group)
-    dist.all_gather(vxs, vx_local.contiguous().view(torch.int32), group=group)
-    return torch.cat(vis), torch.cat(vxs).view(vx_local.dtype)
+    dev = vi_local.device
+    cnt = torch.tensor([vi_local.numel()], dtype=torch.int64, device=dev)
+    cnts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnts, cnt, group=group)
+    sizes = [int(c) for c in cnts.tolist()]
+    cap = max(max(sizes), 1)
+    send = torch.zeros(2 * cap, dtype=torch.int32, device=dev)  # [0, cap): indices, [cap, 2 cap): value bit patterns
+    send[:vi_g.numel()] = vi_g.to(torch.int32)
+    send[cap:cap + vx_local.numel()] = vx_local.contiguous().view(torch.int32)
+    recv = torch.empty(world * 2 * cap, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, 2, cap)
+    vi = torch.cat([recv[p, 0, :sizes[p]] for p in range(world)])
+    vx = torch.cat([recv[p, 1, :sizes[p]] for p in range(world)]).view(vx_local.dtype)
+    return vi.to(vi_g.dtype), vx

@@ -1,0 +1,90 @@
+"""Host-side logic of the single-box multi-GPU sharding (spla_b200/dist.py), on CPU with the gloo backend and world size 2:
+nnz-balanced row blocks + all-gather of result windows for the pull product, nnz-balanced column blocks + frontier exchange for
+the push product. The per-rank arithmetic is done by the C oracle here (no GPU in this test), so what is checked is exactly the
+partition / exchange plumbing that bench.py --gpus N and a multi-GPU traversal rely on."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.oracle import INT, Oracle
+        from spla_b200 import dist as sd
+        from spla_b200 import graphs
+
+        orc = Oracle()
+        n, Ap, Aj = graphs.rmat(10, edge_factor=8, seed=5)  # every rank generates the same graph
+        g = torch.Generator().manual_seed(3)
+        Ax = torch.randint(1, 4, (Aj.numel(),), generator=g, dtype=torch.int32)
+        v = torch.randint(0, 3, (n,), generator=g, dtype=torch.int32)
+        mask = torch.randint(0, 2, (n,), generator=g, dtype=torch.int32)
+        hAp, hAj, hAx = Ap.numpy().astype(np.uint32), Aj.numpy().astype(np.uint32), Ax.numpy()
+
+        # ---- pull: row blocks, in-place windows, all-gather ----
+        b = sd.balanced_boundaries(Ap, world)
+        assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
+        nnz_parts = [int(Ap[b[p + 1]] - Ap[b[p]]) for p in range(world)]
+        assert max(nnz_parts) <= 0.6 * int(Ap[-1]) + int((Ap[1:] - Ap[:-1]).max())  # nnz-balanced, not n-balanced
+        r0, r1 = b[rank], b[rank + 1]
+        Ap_l, Aj_l, Ax_l = sd.row_slice(Ap, Aj, Ax, r0, r1)
+        full = torch.full((n,), -7, dtype=torch.int32)
+        part = orc.mxv_masked(INT, "MULT", "PLUS", "EQZERO", Ap_l.numpy().astype(np.uint32), Aj_l.numpy().astype(np.uint32), Ax_l.numpy(),
+                              v.numpy(), mask[r0:r1].numpy(), 0)
+        full[r0:r1] = torch.from_numpy(part)
+        sd.allgather_windows(full, b)
+        want = orc.mxv_masked(INT, "MULT", "PLUS", "EQZERO", hAp, hAj, hAx, v.numpy(), mask.numpy(), 0)
+        assert np.array_equal(full.numpy(), want), "row-sharded mxv + all-gather differs from the single-device product"
+
+        # ---- push: column blocks, frontier exchange ----
+        cb = sd.column_boundaries(Aj, n, world)
+        c0, c1 = cb[rank], cb[rank + 1]
+        Ap_c, Aj_c, Ax_c = sd.column_slice(Ap, Aj, Ax, c0, c1)
+        vi = torch.nonzero(v == 2).flatten().to(torch.int32)
+        vx = torch.ones(vi.numel(), dtype=torch.int32)
+        ri, rx = orc.vxm_masked(INT, "MULT", "PLUS", "EQZERO", Ap_c.numpy().astype(np.uint32), Aj_c.numpy().astype(np.uint32), Ax_c.numpy(),
+                                c1 - c0, vi.numpy().astype(np.uint32), vx.numpy(), mask[c0:c1].numpy())
+        gi, gx = sd.exchange_frontier(torch.from_numpy(ri.astype(np.int32)), torch.from_numpy(rx), c0)
+        wi, wx = orc.vxm_masked(INT, "MULT", "PLUS", "EQZERO", hAp, hAj, hAx, n, vi.numpy().astype(np.uint32), vx.numpy(), mask.numpy())
+        assert np.array_equal(gi.numpy().astype(np.uint32), wi) and np.array_equal(gx.numpy(), wx), "column-sharded vxm + frontier exchange differs"
+        assert bool((gi[1:] > gi[:-1]).all())  # concatenation of disjoint ordered windows is sorted
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_and_column_sharding_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_balanced_boundaries_edge_cases():
+    from spla_b200 import dist as sd
+
+    Ap = torch.tensor([0, 0, 0, 10, 10, 11, 11], dtype=torch.int64)  # one hub row swallows most targets
+    for parts in (1, 2, 3, 4, 8):
+        b = sd.balanced_boundaries(Ap, parts)
+        assert len(b) == parts + 1 and b[0] == 0 and b[-1] == 6 and all(b[i] <= b[i + 1] for i in range(parts))
+    b = sd.balanced_boundaries(torch.zeros(5, dtype=torch.int64), 4)  # empty matrix
+    assert b[0] == 0 and b[-1] == 4
