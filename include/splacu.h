@@ -70,7 +70,9 @@ SPLACU_API const char* splacu_last_error(void);
 SPLACU_API int         splacu_launch_count(uint64_t* count); /* kernels launched by this library so far */
 /* tuning knobs, read when a matrix handle is created (the reference's counterpart are the vendor heuristics of
  * src/opencl/cl_accelerator.cpp:84-175): "mxv_hub" 0 = off, 1 = auto (default), 2 = always build the hub cache of
- * the pull kernel; "mxv_hub_min_count" = references a column needs to earn a hub slot (default 16) */
+ * the pull kernel; "mxv_hub_min_count" = references a column needs to earn a hub slot (default 16);
+ * "mxv_hub_total" / "mxv_hub_smem" = hub slots in total / staged in shared memory; "mxv_l2_persist" = L2 persisting window
+ * on v; "vxm_selbits" = expand large frontiers against a select(mask) bitmap instead of the mask itself */
 SPLACU_API int         splacu_set_option(const char* name, int64_t value);
 SPLACU_API int         splacu_get_option(const char* name, int64_t* value);
 

@@ -81,7 +81,7 @@ namespace splacu {
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------
@@ -89,6 +89,8 @@ namespace splacu {
         // dense accumulator + touched bitmap (vxm), sized for the largest vector seen
         uint32_t* acc          = nullptr;
         uint32_t* bitmap       = nullptr;
+        uint32_t* sel_bits     = nullptr;// select(mask[j]) bitmap for large frontiers (vxm)
+        uint32_t  cap_sel      = 0;
         uint32_t  cap_n        = 0;      // capacity in elements of acc
         uint32_t  acc_identity = 0;      // bit pattern acc[] is currently filled with
         bool      acc_clean    = false;  // acc[] == identity everywhere and bitmap == 0
@@ -113,6 +115,7 @@ namespace splacu {
 
     int ws_reserve_vector(Workspace* ws, uint32_t n, cudaStream_t s);
     int ws_reserve_blocks(Workspace* ws, uint32_t n_blocks);
+    int ws_reserve_selbits(Workspace* ws, uint32_t n);
     int ws_reserve_pairs(Workspace* ws, size_t n_pairs, size_t n_offsets);
 
     // ---- shared device-side building blocks (defined in vector_ops.cu) -----------------------

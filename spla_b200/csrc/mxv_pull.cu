@@ -23,8 +23,10 @@
 //                       those gathers on chip.
 //   mxv_fixup_kernel    one thread per tile: r[row] of the (at most one) row that starts in the tile and ends later;
 //                       long chains (hub rows) are summed by the whole warp.
-//   mxv_seq_kernel      one thread per row, strict left-to-right fold: the exact path for early_exit and for
-//                       non-associative adds (MINUS, DIV, FIRST, SECOND, BONE, MINUS_POW2).
+//   mxv_early_kernel    early_exit (BFS bottom-up): first qualifying entry of each row, lane-serial for the first 8 entries,
+//                       then warp-cooperative with a ballot (exact for any op pair).
+//   mxv_seq_kernel      one thread per row, strict left-to-right fold: the exact path for non-associative adds
+//                       (MINUS, DIV, FIRST, SECOND, BONE, MINUS_POW2) without early_exit.
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -476,6 +478,76 @@ namespace splacu {
         }
     }
 
+    // early_exit (BFS bottom-up): r[row] = add(init, p_k*) for the FIRST entry k* of the row whose single-term fold differs
+    // from init, else init -- exactly the state of the reference's sequential fold when it breaks (SURVEY 8a note E), for
+    // any op pair. A warp takes 32 rows: every lane scans the first kEarlySerial entries of its own row (most rows of a
+    // dense frontier stop there); rows that are still undecided are then scanned by the whole warp, 128 entries per step,
+    // with a ballot picking the lowest qualifying position -- a hub row costs nnz/128 steps instead of nnz.
+    static constexpr int kEarlySerial = 8;
+    static constexpr int kEarlyUnroll = 4;
+
+    template<typename T, typename S>
+    __global__ void __launch_bounds__(kBlock) mxv_early_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj,
+                                                               const T* __restrict__ Ax, const T* __restrict__ v, const T* __restrict__ mask,
+                                                               T* __restrict__ r, T init, uint32_t n_rows) {
+        const uint32_t lane    = threadIdx.x & 31u;
+        const uint32_t warp    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+        for (uint32_t base = warp * 32u; base < n_rows; base += n_warps * 32u) {
+            const uint32_t row   = base + lane;
+            const bool     valid = row < n_rows;
+            const bool     take  = valid && (sel.reads_mask ? sel.test(mask[row]) : (sel.classes != 0u));
+            uint32_t       k0 = 0, k1 = 0;
+            if (take) {
+                k0 = Ap[row];
+                k1 = Ap[row + 1];
+            }
+            T    res  = init;
+            bool done = true;
+            if (k1 > k0) {
+                const uint32_t kend = min(k1, k0 + (uint32_t) kEarlySerial);
+                done                = (kend == k1);
+                for (uint32_t k = k0; k < kend; ++k) {
+                    const T s = sr.add(init, sr.mult(Ax[k], v[Aj[k]]));
+                    if (value_neq(s, init)) {
+                        res  = s;
+                        done = true;
+                        break;
+                    }
+                }
+            }
+            uint32_t pending = __ballot_sync(0xffffffffu, !done);
+            while (pending) {
+                const int      src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint32_t ks = __shfl_sync(0xffffffffu, k0, src) + (uint32_t) kEarlySerial;
+                const uint32_t ke = __shfl_sync(0xffffffffu, k1, src);
+                bool           hit   = false;
+                T              found = init;
+                for (uint32_t kb = ks; kb < ke && !hit; kb += 32u * kEarlyUnroll) {
+                    T    s[kEarlyUnroll];
+                    bool q[kEarlyUnroll];
+#pragma unroll
+                    for (int u = 0; u < kEarlyUnroll; ++u) {
+                        const uint32_t k = kb + u * 32u + lane;
+                        q[u]             = k < ke;
+                        s[u]             = q[u] ? sr.add(init, sr.mult(Ax[k], v[Aj[k]])) : init;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kEarlyUnroll; ++u) {
+                        const uint32_t m = __ballot_sync(0xffffffffu, q[u] && value_neq(s[u], init));
+                        if (m && !hit) {
+                            found = __shfl_sync(0xffffffffu, s[u], __ffs(m) - 1);
+                            hit   = true;
+                        }
+                    }
+                }
+                if ((int) lane == src && hit) res = found;
+            }
+            if (valid) r[row] = res;
+        }
+    }
+
     template<typename T, typename S, bool MASKED, bool HUB>
     static int launch_wtile(S sr, Select sel, const Csr* M, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
         auto           kern = mxv_wtile_kernel<T, S, MASKED, HUB>;
@@ -576,6 +648,12 @@ extern "C" int splacu_mxv_masked(splacu_csr handle, int dtype, int op_mult, int 
         return dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
             using S = decltype(sr);
             if (!early_exit && is_assoc_commutative(op_add)) return launch_tiles<T, S>(sr, sel, M, v, mask, r, init, s);
+            if (early_exit) {
+                mxv_early_kernel<T, S><<<grid_for((size_t) M->n_rows, kBlock, 8), kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), v,
+                                                                                                   mask, r, init, M->n_rows);
+                SPLACU_LAUNCH_CHECK();
+                return 0;
+            }
             mxv_seq_kernel<T, S><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), v, mask,
                                                                                   r, init, M->n_rows, early_exit);
             SPLACU_LAUNCH_CHECK();

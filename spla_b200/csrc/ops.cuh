@@ -187,10 +187,11 @@ namespace splacu {
     }
 
     // acc[j] = add(acc[j], val) for an associative + commutative add with acc pre-set to the identity
-    template<typename T> __device__ __forceinline__ void atomic_combine(int op, T* addr, T val) {
+    // `cur` is a (possibly stale) value of *addr the caller already loaded: it only serves to skip atomics that cannot
+    // change the accumulator (idempotent ops); a stale value costs at most one redundant atomic.
+    template<typename T> __device__ __forceinline__ void atomic_combine(int op, T* addr, T val, T cur) {
         if constexpr (std::is_floating_point_v<T>) {// float
             float* a = reinterpret_cast<float*>(addr);
-            const float cur = *reinterpret_cast<volatile float*>(addr);
             switch (op) {
                 case SPLACU_PLUS: atomicAdd(a, val); return;
                 case SPLACU_MIN:
@@ -214,7 +215,6 @@ namespace splacu {
             }
         } else if constexpr (std::is_signed_v<T>) {// int32
             int* a = reinterpret_cast<int*>(addr);
-            const int cur = *reinterpret_cast<volatile int*>(addr);
             switch (op) {
                 case SPLACU_PLUS: atomicAdd(a, val); return;
                 case SPLACU_MIN: if (val < cur) atomicMin(a, val); return;
@@ -228,7 +228,6 @@ namespace splacu {
             }
         } else {// uint32
             unsigned int* a = reinterpret_cast<unsigned int*>(addr);
-            const unsigned int cur = *reinterpret_cast<volatile unsigned int*>(addr);
             switch (op) {
                 case SPLACU_PLUS: atomicAdd(a, val); return;
                 case SPLACU_MIN: if (val < cur) atomicMin(a, val); return;

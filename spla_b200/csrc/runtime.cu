@@ -31,8 +31,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto, 2 force*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto, 2 force*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
@@ -54,6 +54,19 @@ namespace splacu {
         SPLACU_CUDA(cudaMemsetAsync(ws->bitmap, 0, words * sizeof(uint32_t), s));
         ws->cap_n     = (uint32_t) cap;
         ws->acc_clean = false;
+        return 0;
+    }
+
+    int ws_reserve_selbits(Workspace* ws, uint32_t n) {
+        if (n <= ws->cap_sel && ws->sel_bits) return 0;
+        if (ws->sel_bits) {
+            SPLACU_CUDA(cudaDeviceSynchronize());
+            cudaFree(ws->sel_bits);
+            ws->sel_bits = nullptr;
+        }
+        const size_t cap = (size_t) n + (n >> 2) + 1024;
+        SPLACU_CUDA(cudaMalloc(&ws->sel_bits, ((cap + 31) / 32 + 1) * sizeof(uint32_t)));
+        ws->cap_sel = (uint32_t) (cap > 0xffffffffull ? 0xffffffffull : cap);
         return 0;
     }
 
@@ -322,7 +335,7 @@ int splacu_workspace_create(splacu_workspace* out) {
 int splacu_workspace_destroy(splacu_workspace handle) {
     if (!handle) return SPLACU_OK;
     Workspace* ws = reinterpret_cast<Workspace*>(handle);
-    cudaFree(ws->acc); cudaFree(ws->bitmap); cudaFree(ws->block_sums); cudaFree(ws->d_scalars);
+    cudaFree(ws->acc); cudaFree(ws->bitmap); cudaFree(ws->sel_bits); cudaFree(ws->block_sums); cudaFree(ws->d_scalars);
     cudaFreeHost(ws->h_scalars);
     cudaFree(ws->keys_a); cudaFree(ws->keys_b); cudaFree(ws->vals_a); cudaFree(ws->vals_b); cudaFree(ws->offsets);
     cudaFree(ws->sort_tmp);

@@ -45,13 +45,17 @@ namespace splacu {
     }
 
     // MODE 0: atomic accumulate into acc + bitmap (fast path). MODE 1: write (key, product) pairs (exact path).
+    // Every thread walks kEpt consecutive edge slots of the expanded frontier: no CTA barrier, 64 fully independent warps per
+    // SM hide the random-access latency. (Measured alternative, dropped: a CTA-tiled variant that stages the frontier entries of
+    // 2048 slots in shared memory and assigns slots round-robin for coalesced Aj loads was 2-3x SLOWER on the 400 M-edge level
+    // of an RMAT-24 BFS -- its barriers serialise the three dependent random accesses of a tile.)
     template<typename T, typename S, int MODE>
     __global__ void __launch_bounds__(kBlock) vxm_expand_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj,
-                                                                const T* __restrict__ Ax, uint32_t nv, const uint32_t* __restrict__ vi,
-                                                                const T* __restrict__ vx, const T* __restrict__ mask,
-                                                                const uint32_t* __restrict__ off /*[nv+1]*/, T* __restrict__ acc,
-                                                                uint32_t* __restrict__ bitmap, uint32_t* __restrict__ keys, T* __restrict__ vals,
-                                                                uint32_t invalid_key) {
+                                                                    const T* __restrict__ Ax, uint32_t nv, const uint32_t* __restrict__ vi,
+                                                                    const T* __restrict__ vx, const T* __restrict__ mask,
+                                                                    const uint32_t* __restrict__ sel_bits, const uint32_t* __restrict__ off /*[nv+1]*/,
+                                                                    T* __restrict__ acc, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ keys,
+                                                                    T* __restrict__ vals, uint32_t invalid_key, uint32_t identity_bits) {
         const uint32_t total = off[nv];
         const uint32_t chunk = kBlock * kEpt;
         for (uint64_t base = (uint64_t) blockIdx.x * chunk; base < total; base += (uint64_t) gridDim.x * chunk) {
@@ -69,20 +73,34 @@ namespace splacu {
                     row0  = Ap[vi[t]] - off[t];
                     x     = vx[t];
                 }
-                const uint32_t k    = row0 + e;
-                const uint32_t j    = Aj[k];
-                const bool     take = sel.reads_mask ? sel.test(mask[j]) : (sel.classes != 0u);
+                const uint32_t k = row0 + e;
+                const uint32_t j = Aj[k];
+                bool           take;
+                if (sel_bits) take = ((sel_bits[j >> 5] >> (j & 31u)) & 1u) != 0u;
+                else take = sel.reads_mask ? sel.test(mask[j]) : (sel.classes != 0u);
                 if (MODE == 0) {
                     if (take) {
-                        atomic_combine<T>(sr.add_op(), &acc[j], sr.mult(x, Ax[k]));
-                        const uint32_t bit = 1u << (j & 31u);
-                        if (!(*reinterpret_cast<volatile uint32_t*>(&bitmap[j >> 5]) & bit)) atomicOr(&bitmap[j >> 5], bit);
+                        const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&acc[j]);
+                        atomic_combine<T>(sr.add_op(), &acc[j], sr.mult(x, Ax[k]), from_bits<T>(cur));
+                        if (cur == identity_bits) atomicOr(&bitmap[j >> 5], 1u << (j & 31u));
                     }
                 } else {
                     keys[e] = take ? j : invalid_key;
                     vals[e] = take ? sr.mult(x, Ax[k]) : T(0);
                 }
             }
+        }
+    }
+
+    // bit j of sel_bits = select(mask[j]): a 2 MB L2-resident stand-in for the 64 MB mask when a large frontier is expanded
+    template<typename T>
+    __global__ void __launch_bounds__(kBlock) select_bits_kernel(Select sel, const T* __restrict__ mask, uint32_t n, uint32_t* __restrict__ sel_bits) {
+        const uint32_t n_pad  = (n + 31) & ~31u;
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+            const bool     p = (i < n) && sel.test(mask[i]);
+            const uint32_t m = __ballot_sync(0xffffffffu, p);
+            if ((threadIdx.x & 31) == 0) sel_bits[i >> 5] = m;
         }
     }
 
@@ -139,10 +157,18 @@ namespace splacu {
                 ws->acc_identity = to_bits(identity);
                 ws->acc_clean    = true;
             }
+            const uint32_t* sel_bits = nullptr;
+            if (sel.reads_mask && get_option(OPT_VXM_SELBITS) && (uint64_t) nv * 64 >= n) {
+                // (nv * 64 >= n: a frontier this large expands to at least ~n edges on the graphs this path sees)
+                if ((rc = ws_reserve_selbits(ws, n))) return rc;
+                select_bits_kernel<T><<<grid_for(n, kBlock, 8), kBlock, 0, s>>>(sel, d_mask, n, ws->sel_bits);
+                SPLACU_LAUNCH_CHECK();
+                sel_bits = ws->sel_bits;
+            }
             rc = dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
                 using S = decltype(sr);
                 vxm_expand_kernel<T, S, 0><<<grid, kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vi, d_vx, d_mask,
-                                                                   ws->offsets, acc, ws->bitmap, nullptr, nullptr, 0u);
+                                                                   sel_bits, ws->offsets, acc, ws->bitmap, nullptr, nullptr, 0u, to_bits(identity));
                 SPLACU_LAUNCH_CHECK();
                 return 0;
             });
@@ -159,8 +185,8 @@ namespace splacu {
                 sr.ad    = op_add;
                 sr.ident = T(0);
                 vxm_expand_kernel<T, SemiringDynamic<T>, 1><<<grid, kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vi, d_vx,
-                                                                                   d_mask, ws->offsets, nullptr, nullptr, ws->keys_a,
-                                                                                   reinterpret_cast<T*>(ws->vals_a), n);
+                                                                                   d_mask, nullptr, ws->offsets, nullptr, nullptr, ws->keys_a,
+                                                                                   reinterpret_cast<T*>(ws->vals_a), n, 0u);
                 SPLACU_LAUNCH_CHECK();
                 int end_bit = 1;
                 while (end_bit < 32 && (n >> end_bit) != 0u) ++end_bit;// keys are in [0, n]

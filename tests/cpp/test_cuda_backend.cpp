@@ -209,7 +209,12 @@ int main(int argc, char** argv) {
             pr(p, A, 0.85f, 1e-6f);
             res[pass] = read_float(p);
         }
-        check(close_rel(res[1], res[0], 1e-5f), "pr : cuda ranks within 1e-5 relative of cpu ranks");
+        // the reference's sequential float fold itself carries up to d * 2^-24 relative error on a row of d entries (the device
+        // sums a row as a tree and is closer to the exact sum), so the 1e-5 bar is widened for graphs with rows that long
+        std::size_t d_max = 0;
+        for (auto& a : g.adj) d_max = std::max(d_max, a.size());
+        const float rtol = std::max(1e-5f, float(d_max) * 1.2e-7f);
+        check(close_rel(res[1], res[0], rtol), "pr : cuda ranks within max(1e-5, d_max * 2^-23) = " + std::to_string(rtol) + " relative of cpu ranks");
     }
 
     // ---- a user-defined op has no device code: the cuda algorithm must say so instead of running on the cpu --------------
