@@ -99,6 +99,9 @@ SPLACU_API int splacu_csr_create(splacu_csr* M, uint32_t n_rows, uint32_t n_cols
 SPLACU_API int splacu_csr_destroy(splacu_csr M);
 /* introspection for tests / logs: nnz tiles of the pull kernel and hub-cache slots (either pointer may be NULL) */
 SPLACU_API int splacu_csr_info(splacu_csr M, uint32_t* n_tiles, uint32_t* n_hub);
+/* column-class phases of the pull kernel (hub classes first, the tail class last): *n_phases = number of classes (0 when
+ * the matrix is processed in one pass), nnz_per_phase[p] = entries of class p for p < min(*n_phases, cap) */
+SPLACU_API int splacu_csr_phases(splacu_csr M, int* n_phases, uint32_t* nnz_per_phase, int cap);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 

@@ -58,6 +58,21 @@ namespace splacu {
     }
 
     // ---- device csr handle ---------------------------------------------------------------
+    // One column class of the matrix (mxv_pull.cu, "column-class phases"): the entries whose column belongs to the class, as a
+    // CSR over all rows. Hub classes index a table of <= 65536 values of v that the kernel keeps in shared memory, so their
+    // column ids are 16-bit slots; the tail class keeps the original 32-bit column ids.
+    struct CsrPhase {
+        uint32_t  nnz = 0, n_tiles = 0;
+        uint32_t  slot_base = 0, n_slots = 0;// hub classes: slots [slot_base, slot_base + n_slots) of hub_cols / hub_vals
+        bool      idx16     = false;
+        uint32_t* Ap        = nullptr;       // [n_rows + 1]
+        void*     Aj        = nullptr;       // uint16 slots (idx16) or uint32 column ids, padded to a whole tile
+        uint32_t* Ax        = nullptr;
+        uint2*    tile_rows = nullptr;
+        uint32_t* carry     = nullptr;
+    };
+    static constexpr int kMaxHubPhases = 16;
+
     struct Csr {
         uint32_t        n_rows = 0, n_cols = 0, nnz = 0;
         const uint32_t* Ap = nullptr;
@@ -76,12 +91,15 @@ namespace splacu {
         uint32_t* hub_cols     = nullptr;// [n_hub] column ids, most referenced first
         uint32_t* hub_vals     = nullptr;// [n_hub] v[hub_cols[s]], packed per call
         uint32_t* Aj_hub       = nullptr;// [nnz] Aj with hub columns replaced by (0x80000000 | slot)
+        // column-class phases (hub classes first, the tail class last); n_phases == 0: single-pass kernel on Ap / Aj / Ax
+        int       n_phases     = 0;
+        CsrPhase  phase[kMaxHubPhases + 1];
     };
 
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------

@@ -31,21 +31,26 @@
 #include "ops.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cstring>
 
 namespace splacu {
 
     static constexpr int      kBlock     = 256;
-    static constexpr int      kWarps     = 24;                   // warps per persistent CTA of the streaming kernel
-    static constexpr int      kThreads   = kWarps * 32;          // 768 threads (80 registers each), one CTA per SM
+    static constexpr int      kWarps     = 24;                   // warps per persistent CTA of the streaming kernel: 768 threads
+                                                                 // (80 registers each), one CTA per SM
+    static constexpr int      kWarpsHub  = 24;                   // warps per CTA of the hub-class phases (no gather latency to hide)
     static constexpr int      kItems     = kMxvTile / 32;        // entries per lane per tile (16)
     static constexpr int      kGroups    = kItems / 4;           // 128-bit groups per lane per tile (4)
-    static constexpr int      kShort     = 32;                   // segments up to this length are folded by one lane
     static constexpr uint32_t kHubFlag   = 0x80000000u;          // Aj_hub entry = kHubFlag | slot
     static constexpr uint32_t kSmemLimit = 227u * 1024u;         // opt-in dynamic shared memory per CTA on sm_100
-    static constexpr uint32_t kProdBytes = kWarps * kMxvTile * 4;// 48 KB of per-warp product slices
+    static constexpr uint32_t kSliceWords = kMxvTile + 16;       // per-warp slice: 512 products + 512 row-end flag bits
+    static constexpr uint32_t kProdBytes = kWarps * kSliceWords * 4;// ~50 KB of per-warp slices
     static constexpr uint32_t kHubCap    = (kSmemLimit - kProdBytes - 1024u) / 4u & ~3u;// hub slots per CTA (~41 K)
+    static constexpr uint32_t kPhaseCap  = (kSmemLimit - kWarpsHub * kSliceWords * 4u) / 4u & ~3u;// slots of one hub class (45 K)
+    static_assert(kWarpsHub * 32 <= 1024 && kPhaseCap <= 65536u, "hub-class slots are 16-bit");
+    enum { MODE_PLAIN = 0, MODE_HUB = 1, MODE_SMEM16 = 2 };
     static_assert(kMxvTile == 512, "warp tile = 32 lanes x 4 groups x 4 entries");
 
     // ---- streaming-load helpers ---------------------------------------------------------------
@@ -62,11 +67,29 @@ namespace splacu {
                      : "l"(p), "l"(pol));
         return r;
     }
+    __device__ __forceinline__ uint2 ld_stream_u2(const uint2* p, uint64_t pol) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+        return r;
+    }
+    __device__ __forceinline__ uint32_t ld_stream_u16(const uint16_t* p, uint64_t pol) {
+        uint16_t r;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(p), "l"(pol));
+        return r;
+    }
     __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p, uint64_t pol) {
         uint32_t r;
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
         return r;
     }
+
+    __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+    // The product slice is written in the streaming layout (lane owns the 16-byte groups c * 32 + lane) and read back in the
+    // blocked layout (lane owns groups 4 * lane .. 4 * lane + 3): group g lives at g ^ ((g >> 3) & 3), which keeps the 8 lanes
+    // of every 128-bit shared-memory phase on 8 different bank groups in both directions.
+    __device__ __forceinline__ uint32_t swz_group(uint32_t g) { return g ^ ((g >> 3) & 3u); }
+    __device__ __forceinline__ uint32_t swz_entry(uint32_t e) { return (swz_group(e >> 2) << 2) | (e & 3u); }
 
     __device__ __forceinline__ uint32_t ld_gather_plain(const uint32_t* p) {
         uint32_t r;
@@ -150,10 +173,157 @@ namespace splacu {
         if (s < n_hub) hub_vals[s] = __ldg(v + hub_cols[s]);
     }
 
+    // ---- column-class phases (built once per matrix) ---------------------------------------------------
+    // Random 4-byte gathers that leave the SM cost one L1->L2 request each (~290 G/s on the whole GPU), streaming the
+    // matrix does not. So the entries are split by the popularity class of their column: class p holds the entries whose
+    // column ranks in [p * S, (p + 1) * S) of the most referenced columns (S <= 49152 values = one shared-memory table),
+    // as its own CSR over all rows with 16-bit slots instead of column ids (6 bytes per entry); the tail class keeps the
+    // rest with 32-bit column ids. Each class is one pass of the streaming kernel; only the tail pass gathers from L2.
+    struct PhasePtrs {
+        uint32_t* Ap[kMaxHubPhases + 1];
+        void*     Aj[kMaxHubPhases + 1];
+        uint32_t* Ax[kMaxHubPhases + 1];
+    };
+    __device__ __forceinline__ uint32_t phase_of(uint32_t slot, uint32_t slots_per_phase, uint32_t n_hub_phases) {
+        return slot == 0xffffffffu ? n_hub_phases : slot / slots_per_phase;
+    }
+    // a warp per row: cnt[p][row] = entries of the row in class p
+    __global__ void __launch_bounds__(kBlock) phase_count_kernel(const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj, uint32_t n_rows,
+                                                                 const uint32_t* __restrict__ slot, uint32_t slots_per_phase, uint32_t n_hub_phases,
+                                                                 uint32_t* __restrict__ cnt) {
+        const uint32_t lane    = threadIdx.x & 31u;
+        const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+        for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
+            const uint32_t k0 = Ap[row], k1 = Ap[row + 1];
+            uint32_t       mine = 0;
+            for (uint32_t kb = k0; kb < k1; kb += 32) {
+                const uint32_t k = kb + lane;
+                const uint32_t p = k < k1 ? phase_of(slot[Aj[k]], slots_per_phase, n_hub_phases) : 0xffu;
+                for (uint32_t q = 0; q <= n_hub_phases; ++q) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, p == q);
+                    if (lane == q) mine += __popc(m);
+                }
+            }
+            if (lane <= n_hub_phases) cnt[(size_t) lane * (n_rows + 1) + row] = mine;
+        }
+    }
+    // a warp per row: stable partition of the row's entries into the class arrays (column order is kept inside a class)
+    __global__ void __launch_bounds__(kBlock) phase_scatter_kernel(const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj,
+                                                                   const uint32_t* __restrict__ Ax, uint32_t n_rows, const uint32_t* __restrict__ slot,
+                                                                   uint32_t slots_per_phase, uint32_t n_hub_phases, PhasePtrs out) {
+        const uint32_t lane    = threadIdx.x & 31u;
+        const uint32_t lt      = (1u << lane) - 1u;
+        const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+        for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
+            const uint32_t k0 = Ap[row], k1 = Ap[row + 1];
+            uint32_t       off = lane <= n_hub_phases ? out.Ap[lane][row] : 0u;// lane q tracks the write position of class q
+            for (uint32_t kb = k0; kb < k1; kb += 32) {
+                const uint32_t k  = kb + lane;
+                const bool     ok = k < k1;
+                uint32_t       col = 0, sl = 0xffffffffu, val = 0;
+                if (ok) {
+                    col = Aj[k];
+                    sl  = slot[col];
+                    val = Ax[k];
+                }
+                const uint32_t p = ok ? phase_of(sl, slots_per_phase, n_hub_phases) : 0xffu;
+                for (uint32_t q = 0; q <= n_hub_phases; ++q) {
+                    const uint32_t m    = __ballot_sync(0xffffffffu, p == q);
+                    const uint32_t base = __shfl_sync(0xffffffffu, off, q);
+                    if (p == q) {
+                        const uint32_t dst = base + __popc(m & lt);
+                        if (q < n_hub_phases) reinterpret_cast<uint16_t*>(out.Aj[q])[dst] = (uint16_t) (sl - q * slots_per_phase);
+                        else reinterpret_cast<uint32_t*>(out.Aj[q])[dst] = col;
+                        out.Ax[q][dst] = val;
+                    }
+                    if (lane == q) off += __popc(m);
+                }
+            }
+        }
+    }
+
+    static void free_phases(Csr* M) {
+        for (int p = 0; p < M->n_phases; ++p) {
+            CsrPhase& ph = M->phase[p];
+            cudaFree(ph.Ap); cudaFree(ph.Aj); cudaFree(ph.Ax); cudaFree(ph.tile_rows); cudaFree(ph.carry);
+            ph = CsrPhase();
+        }
+        M->n_phases = 0;
+    }
+
+    // slot[col] = rank of the column among the n_hub most referenced ones (else 0xffffffff), hub_cols = those columns
+    static int build_phases(Csr* M, const uint32_t* d_slot, uint32_t n_hub, uint32_t slots_per_phase, cudaStream_t s) {
+        const uint32_t n_hub_phases = (n_hub + slots_per_phase - 1) / slots_per_phase;
+        const uint32_t n_classes    = n_hub_phases + 1;
+        const size_t   stride       = (size_t) M->n_rows + 1;
+        uint32_t*      cnt          = nullptr;
+        void*          tmp          = nullptr;
+        int            rc           = 0;
+#define PH_CUDA(expr)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) {                                              \
+            rc = ::splacu::cuda_fail(_e, #expr, __FILE__, __LINE__);          \
+            goto done;                                                        \
+        }                                                                     \
+    } while (0)
+        {
+            PhasePtrs ptrs;
+            memset(&ptrs, 0, sizeof(ptrs));
+            size_t   tmp_bytes = 0;
+            uint32_t totals[kMaxHubPhases + 1];
+            M->n_phases = (int) n_classes;
+            PH_CUDA(cudaMalloc(&cnt, n_classes * stride * 4));
+            PH_CUDA(cudaMemsetAsync(cnt, 0, n_classes * stride * 4, s));
+            phase_count_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->n_rows, d_slot, slots_per_phase, n_hub_phases, cnt);
+            PH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, cnt, (int) stride, s));
+            PH_CUDA(cudaMalloc(&tmp, tmp_bytes));
+            for (uint32_t p = 0; p < n_classes; ++p) {
+                CsrPhase& ph = M->phase[p];
+                PH_CUDA(cudaMalloc(&ph.Ap, stride * 4));
+                PH_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt + p * stride, ph.Ap, (int) stride, s));
+                PH_CUDA(cudaMemcpyAsync(&totals[p], ph.Ap + M->n_rows, 4, cudaMemcpyDeviceToHost, s));
+            }
+            PH_CUDA(cudaStreamSynchronize(s));
+            count_launch(1 + 2 * (int) n_classes);
+            for (uint32_t p = 0; p < n_classes; ++p) {
+                CsrPhase& ph  = M->phase[p];
+                ph.nnz        = totals[p];
+                ph.idx16      = p < n_hub_phases;
+                ph.slot_base  = ph.idx16 ? p * slots_per_phase : 0u;
+                ph.n_slots    = ph.idx16 ? (n_hub - ph.slot_base < slots_per_phase ? n_hub - ph.slot_base : slots_per_phase) : 0u;
+                ph.n_tiles    = (uint32_t) (((uint64_t) ph.nnz + kMxvTile - 1) / kMxvTile);
+                const size_t padded = (size_t) (ph.n_tiles ? ph.n_tiles : 1) * kMxvTile;
+                PH_CUDA(cudaMalloc(&ph.Aj, padded * (ph.idx16 ? 2 : 4)));
+                PH_CUDA(cudaMalloc(&ph.Ax, padded * 4));
+                ptrs.Ap[p] = ph.Ap, ptrs.Aj[p] = ph.Aj, ptrs.Ax[p] = ph.Ax;
+            }
+            phase_scatter_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->Ax, M->n_rows, d_slot, slots_per_phase, n_hub_phases, ptrs);
+            count_launch(1);
+            for (uint32_t p = 0; p < n_classes; ++p) {
+                CsrPhase& ph = M->phase[p];
+                if (ph.n_tiles == 0) continue;
+                PH_CUDA(cudaMalloc(&ph.tile_rows, (size_t) ph.n_tiles * sizeof(uint2)));
+                PH_CUDA(cudaMalloc(&ph.carry, (size_t) ph.n_tiles * 2 * sizeof(uint32_t)));
+                tile_rows_kernel<<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, M->n_rows, kMxvTile, ph.n_tiles, ph.tile_rows);
+                count_launch(1);
+            }
+            PH_CUDA(cudaStreamSynchronize(s));
+            PH_CUDA(cudaGetLastError());
+        }
+    done:
+#undef PH_CUDA
+        cudaFree(cnt);
+        cudaFree(tmp);
+        if (rc) free_phases(M);
+        return rc;
+    }
+
     static int build_hub(Csr* M, cudaStream_t s) {
-        const int mode = (int) get_option(OPT_MXV_HUB);// 0 off, 1 auto, 2 force
+        const int mode = (int) get_option(OPT_MXV_HUB);// 0 off, 1 auto (phases), 2 force the single-pass hub cache, 3 force phases
         if (mode == 0 || !M->vec_ok || M->n_cols >= kHubFlag) return 0;
         if (mode == 1 && (M->nnz < (1u << 22) || M->n_cols < 4 * kHubCap)) return 0;// v already fits on chip / too little work
+        const bool     phases = mode == 1 || mode == 3;
         const uint32_t n = M->n_cols;
         uint32_t *     count = nullptr, *keys = nullptr, *ids = nullptr, *keys_out = nullptr, *ids_out = nullptr;
         void*          tmp   = nullptr;
@@ -181,8 +351,14 @@ namespace splacu {
         HUB_CUDA(cudaMalloc(&tmp, tmp_bytes));
         HUB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, ids, ids_out, (int) n, 0, 32, s));
         count_launch(6);
-        // how many of the top kHubCap columns are referenced often enough to pay for their slot
-        uint32_t cap = (uint32_t) get_option(OPT_MXV_HUB_TOTAL);
+        // how many of the most referenced columns are referenced often enough to pay for their slot
+        uint32_t slots_per_phase = (uint32_t) get_option(OPT_MXV_PHASE_SLOTS) & ~3u;
+        if (slots_per_phase > kPhaseCap) slots_per_phase = kPhaseCap;
+        if (slots_per_phase < 4) slots_per_phase = 4;
+        uint32_t max_phases = (uint32_t) get_option(OPT_MXV_PHASES);
+        if (max_phases > (uint32_t) kMaxHubPhases) max_phases = kMaxHubPhases;
+        if (max_phases < 1) max_phases = 1;
+        uint32_t cap = phases ? max_phases * slots_per_phase : (uint32_t) get_option(OPT_MXV_HUB_TOTAL);
         if (cap > n) cap = n;
         if (cap < 4) cap = 4;
         const uint32_t min_count = (uint32_t) get_option(OPT_MXV_HUB_MIN_COUNT);
@@ -192,20 +368,30 @@ namespace splacu {
         uint32_t n_hub = 0;
         while (n_hub < cap && ~h_keys[n_hub] >= min_count) ++n_hub;
         free(h_keys);
-        if (n_hub >= 64 || mode == 2) {
+        if (n_hub >= 64 || mode >= 2) {
             if (n_hub == 0) n_hub = cap < 4 ? cap : 4;
             HUB_CUDA(cudaMalloc(&M->hub_cols, (size_t) n_hub * 4));
             HUB_CUDA(cudaMalloc(&M->hub_vals, ((size_t) n_hub + 4) * 4));
-            HUB_CUDA(cudaMalloc(&M->Aj_hub, (size_t) M->nnz * 4));
+            HUB_CUDA(cudaMemsetAsync(M->hub_vals, 0, ((size_t) n_hub + 4) * 4, s));
             HUB_CUDA(cudaMemcpyAsync(M->hub_cols, ids_out, (size_t) n_hub * 4, cudaMemcpyDeviceToDevice, s));
             HUB_CUDA(cudaMemsetAsync(count, 0xff, (size_t) n * 4, s));// reuse as the slot map
             hub_slots_kernel<<<(n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->hub_cols, n_hub, count);
-            hub_encode_kernel<<<grid_for(M->nnz, kBlock, 8), kBlock, 0, s>>>(M->Aj, M->nnz, count, M->Aj_hub);
-            count_launch(2);
-            M->n_hub      = n_hub;
-            M->n_hub_smem = (uint32_t) get_option(OPT_MXV_HUB_SMEM) & ~3u;
-            if (M->n_hub_smem > kHubCap) M->n_hub_smem = kHubCap;
-            if (M->n_hub_smem > n_hub) M->n_hub_smem = n_hub & ~3u;
+            count_launch(1);
+            M->n_hub = n_hub;
+            if (phases) {
+                const int rc = build_phases(M, count, n_hub, slots_per_phase, s);
+                if (rc) {
+                    cleanup();
+                    return rc;
+                }
+            } else {
+                HUB_CUDA(cudaMalloc(&M->Aj_hub, (size_t) M->nnz * 4));
+                hub_encode_kernel<<<grid_for(M->nnz, kBlock, 8), kBlock, 0, s>>>(M->Aj, M->nnz, count, M->Aj_hub);
+                count_launch(1);
+                M->n_hub_smem = (uint32_t) get_option(OPT_MXV_HUB_SMEM) & ~3u;
+                if (M->n_hub_smem > kHubCap) M->n_hub_smem = kHubCap;
+                if (M->n_hub_smem > n_hub) M->n_hub_smem = n_hub & ~3u;
+            }
         }
         HUB_CUDA(cudaStreamSynchronize(s));
 #undef HUB_CUDA
@@ -228,195 +414,352 @@ namespace splacu {
     }
 
     // ---- the streaming kernel ------------------------------------------------------------------------
-    template<typename T, typename S, bool MASKED, bool HUB>
-    __global__ void __launch_bounds__(kThreads, 1)
-            mxv_wtile_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj, const T* __restrict__ Ax,
-                             const T* __restrict__ v, const T* __restrict__ mask, T* __restrict__ r, T init, uint32_t nnz, uint32_t n_tiles,
-                             const uint2* __restrict__ tile_rows, T* __restrict__ carry, int vec_ok, const uint32_t* __restrict__ hub_vals,
-                             uint32_t n_hub_smem) {
-        extern __shared__ __align__(16) uint32_t smem[];
-        const uint32_t tid  = threadIdx.x;
-        const uint32_t lane = tid & 31u;
-        const uint32_t warp = tid >> 5;
-        T*             s_prod = reinterpret_cast<T*>(smem) + warp * kMxvTile;// this warp's product slice
-        const T*       s_hub  = reinterpret_cast<const T*>(smem) + kWarps * kMxvTile;
+    // MODE_PLAIN  : Aj = 32-bit column ids, every gather goes to v (L1 / L2)
+    // MODE_HUB    : Aj = Aj_hub (hub columns replaced by slots); slots below n_hub_smem are served from shared memory
+    // MODE_SMEM16 : one hub column class: Aj = 16-bit slots into a table of n_hub_smem values of v held in shared memory,
+    //               no gather ever leaves the SM
+    // accum != 0  : a later column-class phase: r[row] = add(r[row], sum of the class) for the rows that have entries in it
+    // registers of one tile in flight: its Aj / Ax slices (4 x 128 bit each per lane) and its row range
+    template<typename T> struct TileRegs {
+        uint4    j[kGroups], a[kGroups];
+        uint2    rows;
+        bool     streamed;
+        uint32_t a0, b0;// extent of the lane's row in the first 32-row group of the tile
+        bool     take0; // ... its select(mask) ...
+        T        old0;  // ... and its r value (accumulating phases)
+    };
 
-        if (HUB) {// hub values of v -> shared memory, 128-bit coalesced
-            uint4*       dst = reinterpret_cast<uint4*>(smem + kWarps * kMxvTile);
+    template<typename T, typename S, bool MASKED, int MODE, int WARPS>
+    __global__ void __launch_bounds__(WARPS * 32, 1)
+            mxv_wtile_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj, const T* __restrict__ Ax,
+                             const T* __restrict__ v, const T* __restrict__ mask, T* r, T init, uint32_t nnz, uint32_t n_tiles,
+                             const uint2* __restrict__ tile_rows, T* __restrict__ carry, int vec_ok, const uint32_t* __restrict__ hub_vals,
+                             uint32_t n_hub_smem, int accum) {
+        extern __shared__ __align__(16) uint32_t smem[];
+        // DEPTH tiles of Aj / Ax in flight per warp, RPL rows per lane and row-loop step. Both stay at 1: unrolling the tile body
+        // (DEPTH 2, RPL 4: 5.5 K instructions) made the kernel instruction-fetch bound (ncu: stalled_no_instruction 9.6 per issue),
+        // and 16 warps with two tiles in flight by register rotation were slower than 24 warps with one.
+        constexpr int      DEPTH    = 1;
+        constexpr int      RPL      = 1;
+        // a hub class spans many rows per tile (few entries of the class per row): its row loops request the extents of the
+        // next rows before they handle the current ones
+        constexpr bool     ROWPIPE  = MODE == MODE_SMEM16;
+        constexpr uint32_t kThreads = WARPS * 32;
+        const uint32_t     tid      = threadIdx.x;
+        const uint32_t     lane     = tid & 31u;
+        const uint32_t     warp     = tid >> 5;
+        T*                 s_prod   = reinterpret_cast<T*>(smem) + warp * kSliceWords;// this warp's product slice ...
+        uint32_t*          s_flag   = smem + warp * kSliceWords + kMxvTile;           // ... and its row-end flags
+        const T*           s_hub    = reinterpret_cast<const T*>(smem) + WARPS * kSliceWords;
+        const uint16_t*    Aj16     = reinterpret_cast<const uint16_t*>(Aj);
+
+        if (MODE != MODE_PLAIN) {// hub values of v -> shared memory, 128-bit coalesced
+            uint4*       dst = reinterpret_cast<uint4*>(smem + WARPS * kSliceWords);
             const uint4* src = reinterpret_cast<const uint4*>(hub_vals);
-            for (uint32_t i = tid; i < n_hub_smem / 4; i += kThreads) dst[i] = __ldg(src + i);
+            for (uint32_t i = tid; i < (n_hub_smem + 3u) / 4u; i += kThreads) dst[i] = __ldg(src + i);
             __syncthreads();
         }
 
         const bool     all = !MASKED && (sel.classes != 0u);// ALWAYS (NEVER never gets here)
         const uint64_t pol = policy_evict_first();
-        // hub slots below n_hub_smem live in shared memory, the rest of the (dense, packed) hub table is served by L1.
+        // MODE_HUB: hub slots below n_hub_smem live in shared memory, the rest of the (dense, packed) hub table is served by L1.
         // Branch-free: predicated loads.
         const uint32_t s_hub_addr = (uint32_t) __cvta_generic_to_shared(s_hub);
         auto gather = [&](uint32_t j) -> T {
-            if (HUB) return from_bits<T>(gather_hub(j, reinterpret_cast<const uint32_t*>(v), hub_vals, s_hub_addr, n_hub_smem));
+            if (MODE == MODE_SMEM16) return s_hub[j];
+            if (MODE == MODE_HUB) return from_bits<T>(gather_hub(j, reinterpret_cast<const uint32_t*>(v), hub_vals, s_hub_addr, n_hub_smem));
             return from_bits<T>(ld_gather_plain(reinterpret_cast<const uint32_t*>(v) + j));
+        };
+        // the 4 column ids of group c of the tile at entry lo: MODE_SMEM16 keeps them packed (2 x 16 bit in .x and .y)
+        auto load_idx = [&](uint32_t lo, int c) -> uint4 {
+            if (MODE == MODE_SMEM16) {
+                const uint2 q = ld_stream_u2(reinterpret_cast<const uint2*>(Aj16 + lo) + c * 32 + lane, pol);
+                return make_uint4(q.x, q.y, 0u, 0u);
+            }
+            return ld_stream_u4(reinterpret_cast<const uint4*>(Aj + lo) + c * 32 + lane, pol);
         };
 
         // Software pipeline: everything a tile needs from HBM (its row range and, unless the mask is sparse, its Aj / Ax slices)
-        // is requested one tile ahead, before the row folds of the current tile, so that on entry a warp only waits for
-        // its gathers.
-        const uint32_t n_warps = gridDim.x * kWarps;
-        uint4          j[kGroups], a[kGroups];
-        uint2          rows     = make_uint2(0u, 0u);
-        bool           streamed = false;
-        bool           dense    = !MASKED;// masked variant: stream ahead only while the mask keeps selecting most of a tile
-        auto           prefetch = [&](uint32_t t) {
-            streamed = false;
+        // is requested DEPTH tiles ahead, right after the registers of the tile DEPTH back are consumed, so that on entry a
+        // warp only waits for its gathers.
+        const uint32_t n_warps = gridDim.x * WARPS;
+        bool           dense   = !MASKED;// masked variant: stream ahead only while the mask keeps selecting most of a tile
+        uint2          rows_q  = make_uint2(0u, 0u);// tile_rows of the tile the next prefetch() is for, requested a tile earlier
+        auto           prefetch = [&](TileRegs<T>& tr, uint32_t t) {
+            tr.streamed = false;
             if (t >= n_tiles) return;
-            rows = __ldg(tile_rows + t);
+            tr.rows = rows_q;
+            if (t + n_warps < n_tiles) rows_q = __ldg(tile_rows + t + n_warps);
+            // row extents of the first 32 rows of the tile, its mask and (accumulating phases) its r values
+            const uint32_t row = tr.rows.x + lane;
+            tr.a0 = tr.b0 = 0u;
+            tr.take0      = false;
+            tr.old0       = init;
+            if (row < tr.rows.y) {
+                tr.a0    = __ldg(Ap + row);
+                tr.b0    = __ldg(Ap + row + 1);
+                tr.take0 = all ? true : (MASKED ? sel.test(mask[row]) : false);
+                if (accum) tr.old0 = r[row];// r[row] is written by this tile only (border rows go through carry[])
+            }
             if (!dense || !vec_ok || nnz - t * (uint32_t) kMxvTile < (uint32_t) kMxvTile) return;
 #pragma unroll
-            for (int c = 0; c < kGroups; ++c) j[c] = ld_stream_u4(reinterpret_cast<const uint4*>(Aj + t * (uint32_t) kMxvTile) + c * 32 + lane, pol);
+            for (int c = 0; c < kGroups; ++c) tr.j[c] = load_idx(t * (uint32_t) kMxvTile, c);
 #pragma unroll
-            for (int c = 0; c < kGroups; ++c) a[c] = ld_stream_u4(reinterpret_cast<const uint4*>(Ax + t * (uint32_t) kMxvTile) + c * 32 + lane, pol);
-            streamed = true;
+            for (int c = 0; c < kGroups; ++c) tr.a[c] = ld_stream_u4(reinterpret_cast<const uint4*>(Ax + t * (uint32_t) kMxvTile) + c * 32 + lane, pol);
+            tr.streamed = true;
         };
-        prefetch(blockIdx.x * kWarps + warp);
+        TileRegs<T> buf[DEPTH];
+        buf[0].rows = make_uint2(0u, 0u);
+        if (blockIdx.x * WARPS + warp < n_tiles) rows_q = __ldg(tile_rows + blockIdx.x * WARPS + warp);
+        prefetch(buf[0], blockIdx.x * WARPS + warp);
 
-        for (uint32_t tile = blockIdx.x * kWarps + warp; tile < n_tiles; tile += n_warps) {
-            const uint32_t lo        = tile * (uint32_t) kMxvTile;
-            const uint32_t hi        = (nnz - lo > (uint32_t) kMxvTile) ? lo + (uint32_t) kMxvTile : nnz;
-            const uint32_t row_first = rows.x;// first row with entries in this tile (the head row if one reaches in)
-            const uint32_t row_hi    = rows.y;// one past the last row that starts in this tile
+        for (uint32_t tile = blockIdx.x * WARPS + warp; tile < n_tiles; tile += n_warps) {
+            {
+                TileRegs<T>&   tr        = buf[0];
+                const uint32_t lo        = tile * (uint32_t) kMxvTile;
+                const uint32_t hi        = (nnz - lo > (uint32_t) kMxvTile) ? lo + (uint32_t) kMxvTile : nnz;
+                const uint32_t row_first = tr.rows.x;// first row with entries in this tile (the head row if one reaches in)
+                const uint32_t row_hi    = tr.rows.y;// one past the last row that starts in this tile
+                const bool     streamed  = tr.streamed;
 
-            // row extents of the first 32 rows of the tile: requested now, consumed by the folds after the gathers
-            const uint32_t row0   = row_first + lane;
-            const bool     valid0 = row0 < row_hi;
-            uint32_t       a0 = 0, b0 = 0;
-            bool           take0 = false;
-            if (valid0) {
-                a0    = __ldg(Ap + row0);
-                b0    = __ldg(Ap + row0 + 1);
-                take0 = all ? true : (MASKED ? sel.test(mask[row0]) : false);
-            }
+                // row extents of the first 32 rows of the tile: requested a tile ago with the slices
+                uint32_t a0[RPL], b0[RPL];
+                bool     take0[RPL];
+                T        old0[RPL];
+                a0[0] = tr.a0, b0[0] = tr.b0, take0[0] = tr.take0, old0[0] = tr.old0;
 
-            uint32_t need[kGroups];
+                // row-end flags of the tile (bit e: entry e is the last entry of its row inside the tile), set by the lanes that own
+                // the rows, consumed by the segmented scan of phase B
+                if (lane < 16) s_flag[lane] = 0u;
+                __syncwarp();
+                auto mark_end = [&](uint32_t s, uint32_t e) {// [s, e) tile-relative entry range of one row
+                    if (e > s) atomicOr(&s_flag[(e - 1u) >> 5], 1u << ((e - 1u) & 31u));
+                };
+                if (MODE == MODE_SMEM16) {// its tiles span hundreds of rows: pull their extents (and r) into L2 ahead of the row loops
+                    for (uint32_t row = row_first + 32 * RPL + lane * 32; row <= row_hi; row += 32 * 32) prefetch_l2(Ap + row);
+                    if (accum)
+                        for (uint32_t row = row_first + lane * 32; row < row_hi; row += 32 * 32) prefetch_l2(r + row);
+                }
+
+                uint32_t need[kGroups];
 #pragma unroll
-            for (int c = 0; c < kGroups; ++c) need[c] = 0xffffffffu;
-            if (MASKED) {
-                // selected rows mark the 4-entry groups they need: the mask is tested before Aj / Ax / v are touched
+                for (int c = 0; c < kGroups; ++c) need[c] = 0xffffffffu;
+                // a hub class whose slices are already in registers skips this pass (its gathers are on chip and cost nothing):
+                // products of unselected rows are simply never folded; `dense` is then re-estimated by the row loop
+                const bool need_pass = MASKED && !(MODE == MODE_SMEM16 && streamed);
+                if (need_pass) {
+                    // selected rows mark the 4-entry groups they need: the mask is tested before Aj / Ax / v are touched
 #pragma unroll
-                for (int c = 0; c < kGroups; ++c) need[c] = 0u;
-                for (uint32_t row = row0; row < row_hi; row += 32) {
-                    uint32_t ra, rb;
-                    bool     tk;
-                    if (row == row0) {
-                        ra = a0, rb = b0, tk = take0;
-                    } else {
-                        tk = sel.test(mask[row]);
-                        ra = __ldg(Ap + row), rb = __ldg(Ap + row + 1);
+                    for (int c = 0; c < kGroups; ++c) need[c] = 0u;
+                    for (uint32_t row = row_first + lane; row < row_hi; row += 32) {
+                        uint32_t ra, rb;
+                        bool     tk;
+                        if (row == row_first + lane) {
+                            ra = a0[0], rb = b0[0], tk = take0[0];
+                        } else {
+                            tk = sel.test(mask[row]);
+                            ra = __ldg(Ap + row), rb = __ldg(Ap + row + 1);
+                        }
+                        const uint32_t s = max(ra, lo), e = min(rb, hi);
+                        mark_end(s - lo, e > s ? e - lo : s - lo);
+                        if (!tk || e <= s) continue;
+                        const uint32_t g0 = (s - lo) >> 2, g1 = (e - 1 - lo) >> 2;
+#pragma unroll
+                        for (int c = 0; c < kGroups; ++c) {
+                            const uint32_t b0g = max(g0, (uint32_t) c * 32u), b1g = min(g1, (uint32_t) c * 32u + 31u);
+                            if (b0g <= b1g) need[c] |= (0xffffffffu << (b0g & 31u)) & (0xffffffffu >> (31u - (b1g & 31u)));
+                        }
                     }
-                    const uint32_t s = max(ra, lo), e = min(rb, hi);
-                    if (!tk || e <= s) continue;
-                    const uint32_t g0 = (s - lo) >> 2, g1 = (e - 1 - lo) >> 2;
+                    uint32_t n_need = 0;
 #pragma unroll
                     for (int c = 0; c < kGroups; ++c) {
-                        const uint32_t b0g = max(g0, (uint32_t) c * 32u), b1g = min(g1, (uint32_t) c * 32u + 31u);
-                        if (b0g <= b1g) need[c] |= (0xffffffffu << (b0g & 31u)) & (0xffffffffu >> (31u - (b1g & 31u)));
+                        need[c] = __reduce_or_sync(0xffffffffu, need[c]);
+                        n_need += __popc(need[c]);
                     }
+                    dense = n_need >= (uint32_t) (kMxvTile / 8);// at least half of the 128 groups
                 }
-                uint32_t n_need = 0;
-#pragma unroll
-                for (int c = 0; c < kGroups; ++c) {
-                    need[c] = __reduce_or_sync(0xffffffffu, need[c]);
-                    n_need += __popc(need[c]);
-                }
-                dense = n_need >= (uint32_t) (kMxvTile / 8);// at least half of the 128 groups
-            }
 
-            // ---- phase A: stream the tile, gather, multiply, park products in shared memory ----
-            if (vec_ok && hi - lo == (uint32_t) kMxvTile) {
-                T x[kGroups][4];
-                if (!streamed) {
+                // ---- phase A: stream the tile, gather, multiply, park products in shared memory ----
+                if (vec_ok && hi - lo == (uint32_t) kMxvTile) {
+                    T x[kGroups][4];
+                    if (!streamed) {
 #pragma unroll
-                    for (int c = 0; c < kGroups; ++c)
-                        if ((need[c] >> lane) & 1u) j[c] = ld_stream_u4(reinterpret_cast<const uint4*>(Aj + lo) + c * 32 + lane, pol);
+                        for (int c = 0; c < kGroups; ++c)
+                            if ((need[c] >> lane) & 1u) tr.j[c] = load_idx(lo, c);
 #pragma unroll
-                    for (int c = 0; c < kGroups; ++c)
-                        if ((need[c] >> lane) & 1u) a[c] = ld_stream_u4(reinterpret_cast<const uint4*>(Ax + lo) + c * 32 + lane, pol);
-                }
-#pragma unroll
-                for (int c = 0; c < kGroups; ++c)
-                    if ((need[c] >> lane) & 1u) {
-                        x[c][0] = gather(j[c].x);
-                        x[c][1] = gather(j[c].y);
-                        x[c][2] = gather(j[c].z);
-                        x[c][3] = gather(j[c].w);
+                        for (int c = 0; c < kGroups; ++c)
+                            if ((need[c] >> lane) & 1u) tr.a[c] = ld_stream_u4(reinterpret_cast<const uint4*>(Ax + lo) + c * 32 + lane, pol);
                     }
 #pragma unroll
-                for (int c = 0; c < kGroups; ++c)
-                    if ((need[c] >> lane) & 1u) {
-                        uint4 p;
-                        p.x = to_bits(sr.mult(from_bits<T>(a[c].x), x[c][0]));
-                        p.y = to_bits(sr.mult(from_bits<T>(a[c].y), x[c][1]));
-                        p.z = to_bits(sr.mult(from_bits<T>(a[c].z), x[c][2]));
-                        p.w = to_bits(sr.mult(from_bits<T>(a[c].w), x[c][3]));
-                        reinterpret_cast<uint4*>(s_prod)[c * 32 + lane] = p;
-                    }
-            } else {
-                for (uint32_t k = lo + lane; k < hi; k += 32) {
-                    const uint32_t g  = (k - lo) >> 2;
-                    bool           nd = true;
+                    for (int c = 0; c < kGroups; ++c)
+                        if ((need[c] >> lane) & 1u) {
+                            if (MODE == MODE_SMEM16) {
+                                x[c][0] = gather(tr.j[c].x & 0xffffu);
+                                x[c][1] = gather(tr.j[c].x >> 16);
+                                x[c][2] = gather(tr.j[c].y & 0xffffu);
+                                x[c][3] = gather(tr.j[c].y >> 16);
+                            } else {
+                                x[c][0] = gather(tr.j[c].x);
+                                x[c][1] = gather(tr.j[c].y);
+                                x[c][2] = gather(tr.j[c].z);
+                                x[c][3] = gather(tr.j[c].w);
+                            }
+                        }
 #pragma unroll
                     for (int c = 0; c < kGroups; ++c)
-                        if ((g >> 5) == (uint32_t) c) nd = ((need[c] >> (g & 31u)) & 1u) != 0u;
-                    if (nd) s_prod[k - lo] = sr.mult(from_bits<T>(ld_stream_u32(reinterpret_cast<const uint32_t*>(Ax) + k, pol)), gather(ld_stream_u32(Aj + k, pol)));
+                        if ((need[c] >> lane) & 1u) {
+                            uint4 p;
+                            p.x = to_bits(sr.mult(from_bits<T>(tr.a[c].x), x[c][0]));
+                            p.y = to_bits(sr.mult(from_bits<T>(tr.a[c].y), x[c][1]));
+                            p.z = to_bits(sr.mult(from_bits<T>(tr.a[c].z), x[c][2]));
+                            p.w = to_bits(sr.mult(from_bits<T>(tr.a[c].w), x[c][3]));
+                            reinterpret_cast<uint4*>(s_prod)[swz_group(c * 32 + lane)] = p;
+                        }
+                } else {
+                    for (uint32_t k = lo + lane; k < hi; k += 32) {
+                        const uint32_t g  = (k - lo) >> 2;
+                        bool           nd = true;
+#pragma unroll
+                        for (int c = 0; c < kGroups; ++c)
+                            if ((g >> 5) == (uint32_t) c) nd = ((need[c] >> (g & 31u)) & 1u) != 0u;
+                        if (nd) {
+                            const uint32_t col = (MODE == MODE_SMEM16) ? ld_stream_u16(Aj16 + k, pol) : ld_stream_u32(Aj + k, pol);
+                            s_prod[swz_entry(k - lo)] = sr.mult(from_bits<T>(ld_stream_u32(reinterpret_cast<const uint32_t*>(Ax) + k, pol)), gather(col));
+                        }
+                    }
                 }
-            }
-            prefetch(tile + n_warps);
-            __syncwarp();
+                prefetch(tr, tile + n_warps);
+                __syncwarp();
 
-            // ---- phase B: fold the rows of the tile from shared memory ----
-            for (uint32_t base = row_first; base < row_hi; base += 32) {
-                const uint32_t row   = base + lane;
-                const bool     valid = row < row_hi;
-                bool           take = false, head = false, tail = false;
-                uint32_t       s = 0, e = 0;
-                if (valid) {
-                    uint32_t ra, rb;
-                    if (base == row_first) {
-                        ra = a0, rb = b0, take = take0;
-                    } else {
-                        take = all ? true : (MASKED ? sel.test(mask[row]) : false);
-                        ra = __ldg(Ap + row), rb = __ldg(Ap + row + 1);
-                    }
-                    head = ra < lo;
-                    tail = rb > hi;
-                    s    = max(ra, lo) - lo;
-                    e    = min(rb, hi) - lo;
-                    if (!take && !head && !tail) r[row] = init;// partial segments of unselected rows are never read by the fix-up
-                }
-                const bool is_long = valid && take && (e - s > (uint32_t) kShort);
-                if (valid && take && !is_long) {
-                    T acc = sr.identity();
-                    for (uint32_t k = s; k < e; ++k) acc = sr.add(acc, s_prod[k]);
-                    if (head) carry[2 * tile] = acc;
-                    else if (tail) carry[2 * tile + 1] = acc;
-                    else r[row] = (e > s) ? sr.add(init, acc) : init;
-                }
-                uint32_t long_mask = __ballot_sync(0xffffffffu, is_long);
-                while (long_mask) {
-                    const int      src = __ffs(long_mask) - 1;
-                    long_mask &= long_mask - 1;
-                    const uint32_t ls = __shfl_sync(0xffffffffu, s, src), le = __shfl_sync(0xffffffffu, e, src);
-                    T              acc = sr.identity();
-                    for (uint32_t k = ls + lane; k < le; k += 32) acc = sr.add(acc, s_prod[k]);
+                // ---- phase B: segmented sums of the 512 products, one segment per row ----
+                // (1) the lanes that own the rows flag the last entry of every row (done by the need pass when that ran)
+                uint32_t ra[RPL], rb[RPL];
+                bool     tk[RPL];
+                T        old[RPL];
+                auto     load_rows = [&](uint32_t base, bool emit, uint32_t(&xa)[RPL], uint32_t(&xb)[RPL], bool(&xt)[RPL], T(&xo)[RPL]) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc = sr.add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-                    if ((int) lane == src) {
-                        if (head) carry[2 * tile] = acc;
-                        else if (tail) carry[2 * tile + 1] = acc;
-                        else r[row] = sr.add(init, acc);
+                    for (int u = 0; u < RPL; ++u) {
+                        const uint32_t row = base + u * 32 + lane;
+                        xa[u] = xb[u] = 0u;
+                        xt[u]         = false;
+                        xo[u]         = init;
+                        if (row < row_hi) {
+                            xa[u] = __ldg(Ap + row), xb[u] = __ldg(Ap + row + 1);
+                            if (emit) {// the marking pass needs the extents only
+                                xt[u] = all ? true : (MASKED ? sel.test(mask[row]) : false);
+                                if (accum) xo[u] = r[row];
+                            }
+                        }
+                    }
+                };
+                if (!need_pass) {
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u) ra[u] = a0[u], rb[u] = b0[u];
+                    for (uint32_t base = row_first; base < row_hi; base += 32 * RPL) {
+                        uint32_t ran[RPL], rbn[RPL];
+                        bool     tkn[RPL];
+                        T        oldn[RPL];
+                        if (ROWPIPE) load_rows(base + 32 * RPL, false, ran, rbn, tkn, oldn);
+                        else if (base != row_first) load_rows(base, false, ra, rb, tk, old);
+#pragma unroll
+                        for (int u = 0; u < RPL; ++u)
+                            if (base + u * 32 + lane < row_hi) {
+                                const uint32_t s = max(ra[u], lo), e = min(rb[u], hi);
+                                mark_end(s - lo, e > s ? e - lo : s - lo);
+                            }
+                        if (ROWPIPE) {
+#pragma unroll
+                            for (int u = 0; u < RPL; ++u) ra[u] = ran[u], rb[u] = rbn[u];
+                        }
                     }
                 }
+                __syncwarp();
+                // (2) every lane scans its 16 consecutive products: the sum of a segment lands on its flagged entry. Segments that
+                //     span lanes are joined by a warp-level segmented scan of the lanes' open tails (fixed order: deterministic).
+                {
+                    const uint32_t fl = (s_flag[lane >> 1] >> ((lane & 1u) * 16u)) & 0xffffu;
+                    // pass 1: the lane's open tail = sum of the entries after its last flag (all 16 when it has none); the products
+                    // are read 4 at a time, and again in pass 2, rather than held in 16 registers across the warp scan
+                    T open = sr.identity();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 w = reinterpret_cast<const uint4*>(s_prod)[swz_group(4 * lane + q)];
+                        open          = ((fl >> (4 * q + 0)) & 1u) ? sr.identity() : sr.add(open, from_bits<T>(w.x));
+                        open          = ((fl >> (4 * q + 1)) & 1u) ? sr.identity() : sr.add(open, from_bits<T>(w.y));
+                        open          = ((fl >> (4 * q + 2)) & 1u) ? sr.identity() : sr.add(open, from_bits<T>(w.z));
+                        open          = ((fl >> (4 * q + 3)) & 1u) ? sr.identity() : sr.add(open, from_bits<T>(w.w));
+                    }
+                    T    v = open;
+                    bool f = fl != 0u;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const T    vv = __shfl_up_sync(0xffffffffu, v, d);
+                        const bool ff = __shfl_up_sync(0xffffffffu, (int) f, d) != 0;
+                        if ((int) lane >= d) {
+                            if (!f) v = sr.add(vv, v);
+                            f = f || ff;
+                        }
+                    }
+                    T acc = __shfl_up_sync(0xffffffffu, v, 1);// carry-in: open tails of the lanes before, back to the nearest flag
+                    if (lane == 0) acc = sr.identity();
+                    // pass 2: the sum of a segment lands on its flagged (last) entry
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4*      slot = reinterpret_cast<uint4*>(s_prod) + swz_group(4 * lane + q);
+                        const uint4 w    = *slot;
+                        uint4       o    = w;
+                        acc              = sr.add(acc, from_bits<T>(w.x));
+                        if ((fl >> (4 * q + 0)) & 1u) o.x = to_bits(acc), acc = sr.identity();
+                        acc = sr.add(acc, from_bits<T>(w.y));
+                        if ((fl >> (4 * q + 1)) & 1u) o.y = to_bits(acc), acc = sr.identity();
+                        acc = sr.add(acc, from_bits<T>(w.z));
+                        if ((fl >> (4 * q + 2)) & 1u) o.z = to_bits(acc), acc = sr.identity();
+                        acc = sr.add(acc, from_bits<T>(w.w));
+                        if ((fl >> (4 * q + 3)) & 1u) o.w = to_bits(acc), acc = sr.identity();
+                        if ((fl >> (4 * q)) & 15u) *slot = o;
+                    }
+                }
+                __syncwarp();
+                // (3) the lanes that own the rows pick the sums up
+                uint32_t n_sel = 0;// entries of selected rows (re-estimates `dense` when the need pass was skipped)
+#pragma unroll
+                for (int u = 0; u < RPL; ++u) ra[u] = a0[u], rb[u] = b0[u], tk[u] = take0[u], old[u] = old0[u];
+                for (uint32_t base = row_first; base < row_hi; base += 32 * RPL) {
+                    uint32_t ran[RPL], rbn[RPL];
+                    bool     tkn[RPL];
+                    T        oldn[RPL];
+                    if (ROWPIPE) load_rows(base + 32 * RPL, true, ran, rbn, tkn, oldn);
+                    else if (base != row_first) load_rows(base, true, ra, rb, tk, old);
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u) {
+                        const uint32_t row = base + u * 32 + lane;
+                        if (row < row_hi) {
+                            const bool     head = ra[u] < lo, tail = rb[u] > hi;
+                            const uint32_t s = max(ra[u], lo) - lo, e = min(rb[u], hi) - lo;
+                            if (tk[u]) {
+                                if (MASKED && !need_pass) n_sel += e - s;
+                                if (e > s) {
+                                    const T sum = s_prod[swz_entry(e - 1u)];
+                                    if (head) carry[2 * tile] = sum;
+                                    else if (tail) carry[2 * tile + 1] = sum;
+                                    else r[row] = sr.add(accum ? old[u] : init, sum);
+                                } else if (!accum) {
+                                    r[row] = init;
+                                }
+                            } else if (!head && !tail && !accum) {
+                                // partial segments of unselected rows are never read by the fix-up; later phases leave unselected rows alone
+                                r[row] = init;
+                            }
+                        }
+                    }
+                    if (ROWPIPE) {
+#pragma unroll
+                        for (int u = 0; u < RPL; ++u) ra[u] = ran[u], rb[u] = rbn[u], tk[u] = tkn[u], old[u] = oldn[u];
+                    }
+                }
+                if (MASKED && !need_pass) dense = __reduce_add_sync(0xffffffffu, n_sel) * 2u >= hi - lo;
+                __syncwarp();// the product slice is reused by this warp's next tile
             }
-            __syncwarp();// the product slice is reused by this warp's next tile
         }
     }
 
@@ -424,8 +767,8 @@ namespace splacu {
     // One thread per tile; chains longer than 4 tiles (hub rows) are summed by the whole warp in a fixed order.
     template<typename T, typename S>
     __global__ void __launch_bounds__(kBlock) mxv_fixup_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const T* __restrict__ mask,
-                                                               T* __restrict__ r, T init, uint32_t n_tiles, const uint2* __restrict__ tile_rows,
-                                                               const T* __restrict__ carry) {
+                                                               T* r, T init, uint32_t n_tiles, const uint2* __restrict__ tile_rows,
+                                                               const T* __restrict__ carry, int accum) {
         const uint32_t t    = blockIdx.x * blockDim.x + threadIdx.x;
         const uint32_t lane = threadIdx.x & 31u;
         uint32_t       row = 0, chain = 0;// chain = number of later tiles the row reaches into
@@ -437,14 +780,14 @@ namespace splacu {
                 if (end > own && (uint64_t) Ap[row] >= own - kMxvTile) {// starts in this tile, ends later (last tile: end <= nnz <= own)
                     const bool take = sel.reads_mask ? sel.test(mask[row]) : (sel.classes != 0u);
                     if (take) chain = (uint32_t) ((end - own + kMxvTile - 1) / kMxvTile);
-                    else r[row] = init;
+                    else if (!accum) r[row] = init;
                 }
             }
         }
         if (chain > 0 && chain <= 4) {
             T acc = carry[2 * t + 1];
             for (uint32_t u = 1; u <= chain; ++u) acc = sr.add(acc, carry[2 * (t + u)]);
-            r[row] = sr.add(init, acc);
+            r[row] = sr.add(accum ? r[row] : init, acc);
         }
         uint32_t long_mask = __ballot_sync(0xffffffffu, chain > 4);
         while (long_mask) {
@@ -455,7 +798,7 @@ namespace splacu {
             for (uint32_t u = 1 + lane; u <= len; u += 32) acc = sr.add(acc, carry[2 * (t0 + u)]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc = sr.add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-            if ((int) lane == src) r[row] = sr.add(init, sr.add(carry[2 * t + 1], acc));
+            if ((int) lane == src) r[row] = sr.add(accum ? r[row] : init, sr.add(carry[2 * t + 1], acc));
         }
     }
 
@@ -548,21 +891,45 @@ namespace splacu {
         }
     }
 
-    template<typename T, typename S, bool MASKED, bool HUB>
-    static int launch_wtile(S sr, Select sel, const Csr* M, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
-        auto           kern = mxv_wtile_kernel<T, S, MASKED, HUB>;
-        const uint32_t smem = kProdBytes + (HUB ? M->n_hub_smem * 4u : 0u);
+    // one pass of the streaming kernel + its border fix-up over a CSR (the whole matrix or one column class)
+    struct TileJob {
+        const uint32_t* Ap;
+        const void*     Aj;
+        const uint32_t* Ax;
+        uint32_t        nnz, n_tiles;
+        const uint2*    tile_rows;
+        uint32_t*       carry;
+        int             vec_ok;
+        const uint32_t* hub_vals;// table base for MODE_HUB / MODE_SMEM16
+        uint32_t        n_smem;  // slots staged in shared memory
+        int             accum;
+    };
+
+    template<typename T, typename S, bool MASKED, int MODE, int WARPS>
+    static int launch_wtile(S sr, Select sel, const TileJob& job, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
+        auto           kern = mxv_wtile_kernel<T, S, MASKED, MODE, WARPS>;
+        const uint32_t smem = (uint32_t) WARPS * kSliceWords * 4u + (MODE != MODE_PLAIN ? ((job.n_smem + 3u) & ~3u) * 4u : 0u);
         static bool    attr_done = false;// per instantiation
         if (!attr_done) {
             SPLACU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemLimit));
             attr_done = true;
         }
-        const uint32_t want = (M->n_tiles + kWarps - 1) / kWarps;
+        const uint32_t want = (job.n_tiles + WARPS - 1) / WARPS;
         const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
-        kern<<<grid, kThreads, smem, s>>>(sr, sel, M->Ap, HUB ? M->Aj_hub : M->Aj, reinterpret_cast<const T*>(M->Ax), v, mask, r, init, M->nnz,
-                                         M->n_tiles, M->tile_rows, reinterpret_cast<T*>(M->carry), (int) M->vec_ok, M->hub_vals, M->n_hub_smem);
+        kern<<<grid, WARPS * 32, smem, s>>>(sr, sel, job.Ap, reinterpret_cast<const uint32_t*>(job.Aj), reinterpret_cast<const T*>(job.Ax), v, mask, r, init,
+                                            job.nnz, job.n_tiles, job.tile_rows, reinterpret_cast<T*>(job.carry), job.vec_ok, job.hub_vals, job.n_smem,
+                                            job.accum);
+        SPLACU_LAUNCH_CHECK();
+        mxv_fixup_kernel<T, S><<<(job.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, job.Ap, mask, r, init, job.n_tiles, job.tile_rows,
+                                                                                     reinterpret_cast<const T*>(job.carry), job.accum);
         SPLACU_LAUNCH_CHECK();
         return 0;
+    }
+
+    template<typename T, typename S, int MODE, int WARPS>
+    static int launch_job(S sr, Select sel, const TileJob& job, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
+        return sel.reads_mask ? launch_wtile<T, S, true, MODE, WARPS>(sr, sel, job, v, mask, r, init, s)
+                              : launch_wtile<T, S, false, MODE, WARPS>(sr, sel, job, v, mask, r, init, s);
     }
 
     // keep v resident in L2 while the CSR arrays stream through it (access-policy window on the launching stream)
@@ -606,15 +973,27 @@ namespace splacu {
         if (M->n_hub) {
             mxv_hub_pack_kernel<<<(M->n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->hub_cols, M->n_hub, reinterpret_cast<const uint32_t*>(v), M->hub_vals);
             SPLACU_LAUNCH_CHECK();
-            rc = sel.reads_mask ? launch_wtile<T, S, true, true>(sr, sel, M, v, mask, r, init, s) : launch_wtile<T, S, false, true>(sr, sel, M, v, mask, r, init, s);
-        } else {
-            rc = sel.reads_mask ? launch_wtile<T, S, true, false>(sr, sel, M, v, mask, r, init, s) : launch_wtile<T, S, false, false>(sr, sel, M, v, mask, r, init, s);
         }
-        if (rc) return rc;
-        mxv_fixup_kernel<T, S><<<(M->n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, M->Ap, mask, r, init, M->n_tiles, M->tile_rows,
-                                                                                    reinterpret_cast<const T*>(M->carry));
-        SPLACU_LAUNCH_CHECK();
-        return 0;
+        if (M->n_phases) {
+            // column classes, hottest first: the hub classes gather from shared memory only, the tail class from v.
+            // The first non-empty class writes every row, the later ones accumulate onto it in this fixed order.
+            int       accum = 0;
+            const int only  = (int) get_option(OPT_MXV_PHASE_ONLY);
+            for (int p = 0; p < M->n_phases; ++p) {
+                const CsrPhase& ph = M->phase[p];
+                if (ph.nnz == 0 || (only && only != p + 1)) continue;
+                if (only) accum = p > 0;
+                const TileJob job = {ph.Ap, ph.Aj, ph.Ax, ph.nnz, ph.n_tiles, ph.tile_rows, ph.carry, 1, M->hub_vals + ph.slot_base, ph.n_slots, accum};
+                rc = ph.idx16 ? launch_job<T, S, MODE_SMEM16, kWarpsHub>(sr, sel, job, v, mask, r, init, s)
+                              : launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, s);
+                if (rc) return rc;
+                accum = 1;
+            }
+            return 0;
+        }
+        const TileJob job = {M->Ap, M->n_hub ? M->Aj_hub : M->Aj, M->Ax, M->nnz, M->n_tiles, M->tile_rows, M->carry, (int) M->vec_ok, M->hub_vals, M->n_hub_smem, 0};
+        return M->n_hub ? launch_job<T, S, MODE_HUB, kWarps>(sr, sel, job, v, mask, r, init, s)
+                        : launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, s);
     }
 
 }// namespace splacu

@@ -31,8 +31,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto, 2 force*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
@@ -225,6 +225,15 @@ int splacu_csr_info(splacu_csr handle, uint32_t* n_tiles, uint32_t* n_hub) {
     return SPLACU_OK;
 }
 
+int splacu_csr_phases(splacu_csr handle, int* n_phases, uint32_t* nnz_per_phase, int cap) {
+    SPLACU_REQUIRE(handle, "null matrix handle");
+    const Csr* M = reinterpret_cast<const Csr*>(handle);
+    if (n_phases) *n_phases = M->n_phases;
+    if (nnz_per_phase)
+        for (int p = 0; p < M->n_phases && p < cap; ++p) nnz_per_phase[p] = M->phase[p].nnz;
+    return SPLACU_OK;
+}
+
 int splacu_malloc(void** d_ptr, size_t bytes) {
     SPLACU_CHECK_INIT();
     SPLACU_REQUIRE(d_ptr, "null pointer");
@@ -312,6 +321,10 @@ int splacu_csr_destroy(splacu_csr handle) {
     if (M->hub_cols) cudaFree(M->hub_cols);
     if (M->hub_vals) cudaFree(M->hub_vals);
     if (M->Aj_hub) cudaFree(M->Aj_hub);
+    for (int p = 0; p < M->n_phases; ++p) {
+        CsrPhase& ph = M->phase[p];
+        cudaFree(ph.Ap); cudaFree(ph.Aj); cudaFree(ph.Ax); cudaFree(ph.tile_rows); cudaFree(ph.carry);
+    }
     cudaGetLastError();
     delete M;
     return SPLACU_OK;

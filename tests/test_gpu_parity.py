@@ -178,6 +178,92 @@ def test_pull_hub_cache_forced(backend, oracle, dtype, om, oa, osel, hub_smem, h
         assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"hub mxv rep {rep}")
 
 
+def _skewed_csr(rng, dtype, n_rows, n_cols, kind, avg=30):
+    Ap, Aj, Ax = cases.rand_csr(rng, dtype, n_rows, n_cols, avg, skew=True, kind=kind)
+    hubs = rng.integers(0, n_cols, 40, dtype=np.int64)
+    fold = rng.random(len(Aj)) < 0.6
+    Aj = Aj.astype(np.int64)
+    Aj[fold] = hubs[rng.integers(0, len(hubs), int(fold.sum()))]
+    rows = np.repeat(np.arange(n_rows, dtype=np.int64), np.diff(Ap.astype(np.int64)))
+    key, first = np.unique(rows * n_cols + Aj, return_index=True)
+    Aj, Ax, rows = (key % n_cols).astype(np.uint32), Ax[first], key // n_cols
+    Ap = np.zeros(n_rows + 1, dtype=np.uint32)
+    Ap[1:] = np.cumsum(np.bincount(rows, minlength=n_rows))
+    return Ap, Aj, Ax
+
+
+@pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "MULT", "PLUS", "EQZERO"), (UINT, "BAND", "BOR", "ALWAYS"), (FLOAT, "MULT", "PLUS", "ALWAYS"),
+                                               (FLOAT, "PLUS", "MIN", "NQZERO"), (INT, "LAND", "LOR", "GTZERO"), (FLOAT, "MULT", "PLUS", "NQZERO")])
+@pytest.mark.parametrize("slots,phases,min_count", [(4, 1, 2), (16, 3, 2), (64, 16, 1), (1024, 2, 2), (49152, 4, 1)])
+def test_pull_column_class_phases_forced(backend, oracle, dtype, om, oa, osel, slots, phases, min_count):
+    """The column-class phases of the streaming pull kernel (hub classes with 16-bit slots gathered from shared memory, then
+    the tail class, each accumulating onto r) are normally reserved for large matrices; force them on small skewed ones --
+    including classes that end up empty, rows longer than a tile and rows with entries in a single class -- and compare
+    with the oracle."""
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, om, oa, slots, phases)).encode()))
+    n_rows, n_cols = 3000, 2500
+    kind = "positive" if (om, oa) == ("PLUS", "MIN") else ("unit" if dtype == FLOAT else "small")
+    Ap, Aj, Ax = _skewed_csr(rng, dtype, n_rows, n_cols, kind)
+    try:
+        backend.set_option("mxv_hub", 3)
+        backend.set_option("mxv_phase_slots", slots)
+        backend.set_option("mxv_phases", phases)
+        backend.set_option("mxv_hub_min_count", min_count)
+        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+        info = backend.csr_info(M)
+        assert len(info["phase_nnz"]) >= 2 and sum(info["phase_nnz"]) == len(Aj), info
+        assert info["phase_nnz"][0] > 0
+    finally:
+        backend.set_option("mxv_hub", 1)
+        backend.set_option("mxv_phase_slots", 45056)
+        backend.set_option("mxv_phases", 4)
+        backend.set_option("mxv_hub_min_count", 16)
+    for rep in range(2):
+        v = cases.rand_values(rng, dtype, n_cols, kind)
+        mask = cases.rand_values(rng, dtype, n_rows)
+        init = np.float32(3.0e38) if (om, oa) == ("PLUS", "MIN") else (0 if rep == 0 else 3)
+        want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
+        got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
+        backend.sync()
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"phases mxv rep {rep}")
+    # early exit and non-associative adds keep using the original CSR of the handle
+    v = cases.rand_values(rng, dtype, n_cols, kind)
+    mask = cases.rand_values(rng, dtype, n_rows)
+    want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, 0, True)
+    got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, 0, early_exit=True)
+    backend.sync()
+    assert np.array_equal(to_np(got, cases.NP[dtype]), want)
+
+
+def test_pull_column_class_phases_auto(backend, oracle):
+    """A matrix large enough for the automatic choice (>= 4 Mi entries, >= 164 K columns): classes are built without any
+    option, the result matches the oracle (INT: bit-exact, FLOAT: 1e-5)."""
+    rng = np.random.default_rng(77)
+    n = 1 << 18
+    nnz_target = 5 << 20
+    # power-law column popularity, uniform rows
+    rows = rng.integers(0, n, nnz_target, dtype=np.int64)
+    cols = (n * rng.random(nnz_target) ** 4).astype(np.int64)
+    perm = rng.permutation(n)
+    cols = perm[cols]
+    key = np.unique(rows * n + cols)
+    rows, cols = key // n, (key % n).astype(np.uint32)
+    Ap = np.zeros(n + 1, dtype=np.uint32)
+    Ap[1:] = np.cumsum(np.bincount(rows, minlength=n))
+    assert len(cols) >= (1 << 22)
+    for dtype, om, oa, osel in [(INT, "MULT", "PLUS", "NQZERO"), (FLOAT, "MULT", "PLUS", "ALWAYS")]:
+        Ax = cases.rand_values(rng, dtype, len(cols), "unit" if dtype == FLOAT else "small")
+        M = make_csr(backend, n, n, Ap, cols, Ax)
+        info = backend.csr_info(M)
+        assert len(info["phase_nnz"]) >= 2 and sum(info["phase_nnz"]) == len(cols), info
+        v = cases.rand_values(rng, dtype, n, "unit" if dtype == FLOAT else "small")
+        mask = cases.rand_values(rng, dtype, n)
+        want = oracle.mxv_masked(dtype, om, oa, osel, Ap, cols, Ax, v, mask, 1, False)
+        got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, 1)
+        backend.sync()
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"auto phases {dtype}")
+
+
 def test_edge_cases(backend, oracle):
     # empty matrix: every r[i] = init (SURVEY 8a note B); empty frontier; NEVER; explicit zero frontier values (note F)
     e = np.zeros(0, dtype=np.uint32)
