@@ -70,8 +70,33 @@ namespace splacu {
         uint32_t* Ax        = nullptr;
         uint2*    tile_rows = nullptr;
         uint32_t* carry     = nullptr;
+        // segmented-tile format (mxv_seg.cu): Aj / Ax hold the entries lane-blocked per 512-entry tile (a coalesced 128-bit
+        // load hands every lane 16 consecutive entries of the row order), Ap / tile_rows / carry are not kept
+        bool      seg       = false;
+        uint32_t  n_segs    = 0;             // non-empty rows of the class = row segments
+        uint32_t* flags     = nullptr;       // [n_tiles * 16] bit (lane * 16 + i): entry (lane, i) is the last entry of its row
+        uint32_t* seg_base  = nullptr;       // [n_tiles + 1] segments that end before tile t
+        uint32_t* seg_row   = nullptr;       // [n_segs] row of every segment, ascending
+        uint32_t* chain     = nullptr;       // [n_tiles] bit 31: the tile starts inside a row of the previous tile; low bits: tiles
+                                             //           before t that hold the head of the row ending at t's first flag (0: none)
+        uint32_t* head      = nullptr;       // [n_tiles] sum of the tile's first segment when it continues a row (per call)
+        uint32_t* tail      = nullptr;       // [n_tiles] sum after the tile's last flag (per call)
     };
     static constexpr int kMaxHubPhases = 16;
+
+    // storage position of entry e (row order inside a class) in the lane-blocked tile layout: 4-byte items / 2-byte items
+    __host__ __device__ __forceinline__ uint32_t seg_pos32(uint32_t e) {
+        return (e & ~511u) + (((((e & 15u) >> 2) * 32u) + ((e & 511u) >> 4)) << 2) + (e & 3u);
+    }
+    __host__ __device__ __forceinline__ uint32_t seg_pos16(uint32_t e) {
+        return (e & ~511u) + (((((e & 15u) >> 3) * 32u) + ((e & 511u) >> 4)) << 3) + (e & 7u);
+    }
+    struct Select;
+    struct Csr;
+    // mxv_seg.cu: build the segment metadata of a class from its row extents (ph.Ap) and row counts; run all classes
+    int seg_build(const Csr* M, CsrPhase& ph, const uint32_t* d_row_count, cudaStream_t s);
+    int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r,
+                uint32_t init_bits, const uint32_t* gate, uint32_t gate_min, cudaStream_t s);
 
     struct Csr {
         uint32_t        n_rows = 0, n_cols = 0, nnz = 0;
@@ -94,12 +119,13 @@ namespace splacu {
         // column-class phases (hub classes first, the tail class last); n_phases == 0: single-pass kernel on Ap / Aj / Ax
         int       n_phases     = 0;
         CsrPhase  phase[kMaxHubPhases + 1];
+        uint32_t* sel_count    = nullptr;// device counter: rows the mask of the current call selects (chooses the masked path on the device)
     };
 
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------

@@ -210,7 +210,7 @@ namespace splacu {
     // a warp per row: stable partition of the row's entries into the class arrays (column order is kept inside a class)
     __global__ void __launch_bounds__(kBlock) phase_scatter_kernel(const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj,
                                                                    const uint32_t* __restrict__ Ax, uint32_t n_rows, const uint32_t* __restrict__ slot,
-                                                                   uint32_t slots_per_phase, uint32_t n_hub_phases, PhasePtrs out) {
+                                                                   uint32_t slots_per_phase, uint32_t n_hub_phases, PhasePtrs out, int seg) {
         const uint32_t lane    = threadIdx.x & 31u;
         const uint32_t lt      = (1u << lane) - 1u;
         const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -231,10 +231,10 @@ namespace splacu {
                     const uint32_t m    = __ballot_sync(0xffffffffu, p == q);
                     const uint32_t base = __shfl_sync(0xffffffffu, off, q);
                     if (p == q) {
-                        const uint32_t dst = base + __popc(m & lt);
-                        if (q < n_hub_phases) reinterpret_cast<uint16_t*>(out.Aj[q])[dst] = (uint16_t) (sl - q * slots_per_phase);
-                        else reinterpret_cast<uint32_t*>(out.Aj[q])[dst] = col;
-                        out.Ax[q][dst] = val;
+                        const uint32_t dst = base + __popc(m & lt);// position in the row order of the class
+                        if (q < n_hub_phases) reinterpret_cast<uint16_t*>(out.Aj[q])[seg ? seg_pos16(dst) : dst] = (uint16_t) (sl - q * slots_per_phase);
+                        else reinterpret_cast<uint32_t*>(out.Aj[q])[seg ? seg_pos32(dst) : dst] = col;
+                        out.Ax[q][seg ? seg_pos32(dst) : dst] = val;
                     }
                     if (lane == q) off += __popc(m);
                 }
@@ -246,6 +246,7 @@ namespace splacu {
         for (int p = 0; p < M->n_phases; ++p) {
             CsrPhase& ph = M->phase[p];
             cudaFree(ph.Ap); cudaFree(ph.Aj); cudaFree(ph.Ax); cudaFree(ph.tile_rows); cudaFree(ph.carry);
+            cudaFree(ph.flags); cudaFree(ph.seg_base); cudaFree(ph.seg_row); cudaFree(ph.chain); cudaFree(ph.head); cudaFree(ph.tail);
             ph = CsrPhase();
         }
         M->n_phases = 0;
@@ -272,6 +273,7 @@ namespace splacu {
             memset(&ptrs, 0, sizeof(ptrs));
             size_t   tmp_bytes = 0;
             uint32_t totals[kMaxHubPhases + 1];
+            const int seg = get_option(OPT_MXV_SEG) ? 1 : 0;
             M->n_phases = (int) n_classes;
             PH_CUDA(cudaMalloc(&cnt, n_classes * stride * 4));
             PH_CUDA(cudaMemsetAsync(cnt, 0, n_classes * stride * 4, s));
@@ -296,13 +298,21 @@ namespace splacu {
                 const size_t padded = (size_t) (ph.n_tiles ? ph.n_tiles : 1) * kMxvTile;
                 PH_CUDA(cudaMalloc(&ph.Aj, padded * (ph.idx16 ? 2 : 4)));
                 PH_CUDA(cudaMalloc(&ph.Ax, padded * 4));
+                if (seg) {// the padding of the last tile is read by the kernel
+                    PH_CUDA(cudaMemsetAsync(ph.Aj, 0, padded * (ph.idx16 ? 2 : 4), s));
+                    PH_CUDA(cudaMemsetAsync(ph.Ax, 0, padded * 4, s));
+                }
                 ptrs.Ap[p] = ph.Ap, ptrs.Aj[p] = ph.Aj, ptrs.Ax[p] = ph.Ax;
             }
-            phase_scatter_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->Ax, M->n_rows, d_slot, slots_per_phase, n_hub_phases, ptrs);
+            phase_scatter_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->Ax, M->n_rows, d_slot, slots_per_phase, n_hub_phases, ptrs, seg);
             count_launch(1);
             for (uint32_t p = 0; p < n_classes; ++p) {
                 CsrPhase& ph = M->phase[p];
                 if (ph.n_tiles == 0) continue;
+                if (seg) {
+                    if ((rc = seg_build(M, ph, cnt + p * stride, s))) goto done;
+                    continue;
+                }
                 PH_CUDA(cudaMalloc(&ph.tile_rows, (size_t) ph.n_tiles * sizeof(uint2)));
                 PH_CUDA(cudaMalloc(&ph.carry, (size_t) ph.n_tiles * 2 * sizeof(uint32_t)));
                 tile_rows_kernel<<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, M->n_rows, kMxvTile, ph.n_tiles, ph.tile_rows);
@@ -384,6 +394,7 @@ namespace splacu {
                     cleanup();
                     return rc;
                 }
+                HUB_CUDA(cudaMalloc(&M->sel_count, 4));
             } else {
                 HUB_CUDA(cudaMalloc(&M->Aj_hub, (size_t) M->nnz * 4));
                 hub_encode_kernel<<<grid_for(M->nnz, kBlock, 8), kBlock, 0, s>>>(M->Aj, M->nnz, count, M->Aj_hub);
@@ -424,9 +435,6 @@ namespace splacu {
         uint4    j[kGroups], a[kGroups];
         uint2    rows;
         bool     streamed;
-        uint32_t a0, b0;// extent of the lane's row in the first 32-row group of the tile
-        bool     take0; // ... its select(mask) ...
-        T        old0;  // ... and its r value (accumulating phases)
     };
 
     template<typename T, typename S, bool MASKED, int MODE, int WARPS>
@@ -434,8 +442,9 @@ namespace splacu {
             mxv_wtile_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj, const T* __restrict__ Ax,
                              const T* __restrict__ v, const T* __restrict__ mask, T* r, T init, uint32_t nnz, uint32_t n_tiles,
                              const uint2* __restrict__ tile_rows, T* __restrict__ carry, int vec_ok, const uint32_t* __restrict__ hub_vals,
-                             uint32_t n_hub_smem, int accum) {
+                             uint32_t n_hub_smem, int accum, const uint32_t* __restrict__ gate, uint32_t gate_max) {
         extern __shared__ __align__(16) uint32_t smem[];
+        if (gate && *gate >= gate_max) return;// dense mask: the column-class passes (mxv_seg.cu) run instead
         // DEPTH tiles of Aj / Ax in flight per warp, RPL rows per lane and row-loop step. Both stay at 1: unrolling the tile body
         // (DEPTH 2, RPL 4: 5.5 K instructions) made the kernel instruction-fetch bound (ncu: stalled_no_instruction 9.6 per issue),
         // and 16 warps with two tiles in flight by register rotation were slower than 24 warps with one.
@@ -484,23 +493,10 @@ namespace splacu {
         // warp only waits for its gathers.
         const uint32_t n_warps = gridDim.x * WARPS;
         bool           dense   = !MASKED;// masked variant: stream ahead only while the mask keeps selecting most of a tile
-        uint2          rows_q  = make_uint2(0u, 0u);// tile_rows of the tile the next prefetch() is for, requested a tile earlier
         auto           prefetch = [&](TileRegs<T>& tr, uint32_t t) {
             tr.streamed = false;
             if (t >= n_tiles) return;
-            tr.rows = rows_q;
-            if (t + n_warps < n_tiles) rows_q = __ldg(tile_rows + t + n_warps);
-            // row extents of the first 32 rows of the tile, its mask and (accumulating phases) its r values
-            const uint32_t row = tr.rows.x + lane;
-            tr.a0 = tr.b0 = 0u;
-            tr.take0      = false;
-            tr.old0       = init;
-            if (row < tr.rows.y) {
-                tr.a0    = __ldg(Ap + row);
-                tr.b0    = __ldg(Ap + row + 1);
-                tr.take0 = all ? true : (MASKED ? sel.test(mask[row]) : false);
-                if (accum) tr.old0 = r[row];// r[row] is written by this tile only (border rows go through carry[])
-            }
+            tr.rows = __ldg(tile_rows + t);
             if (!dense || !vec_ok || nnz - t * (uint32_t) kMxvTile < (uint32_t) kMxvTile) return;
 #pragma unroll
             for (int c = 0; c < kGroups; ++c) tr.j[c] = load_idx(t * (uint32_t) kMxvTile, c);
@@ -510,7 +506,6 @@ namespace splacu {
         };
         TileRegs<T> buf[DEPTH];
         buf[0].rows = make_uint2(0u, 0u);
-        if (blockIdx.x * WARPS + warp < n_tiles) rows_q = __ldg(tile_rows + blockIdx.x * WARPS + warp);
         prefetch(buf[0], blockIdx.x * WARPS + warp);
 
         for (uint32_t tile = blockIdx.x * WARPS + warp; tile < n_tiles; tile += n_warps) {
@@ -522,11 +517,23 @@ namespace splacu {
                 const uint32_t row_hi    = tr.rows.y;// one past the last row that starts in this tile
                 const bool     streamed  = tr.streamed;
 
-                // row extents of the first 32 rows of the tile: requested a tile ago with the slices
+                // row extents of the first 32 rows of the tile: requested now, consumed after the gathers
                 uint32_t a0[RPL], b0[RPL];
                 bool     take0[RPL];
                 T        old0[RPL];
-                a0[0] = tr.a0, b0[0] = tr.b0, take0[0] = tr.take0, old0[0] = tr.old0;
+#pragma unroll
+                for (int u = 0; u < RPL; ++u) {
+                    const uint32_t row = row_first + u * 32 + lane;
+                    a0[u] = b0[u] = 0u;
+                    take0[u]      = false;
+                    old0[u]       = init;
+                    if (row < row_hi) {
+                        a0[u]    = __ldg(Ap + row);
+                        b0[u]    = __ldg(Ap + row + 1);
+                        take0[u] = all ? true : (MASKED ? sel.test(mask[row]) : false);
+                        if (accum) old0[u] = r[row];
+                    }
+                }
 
                 // row-end flags of the tile (bit e: entry e is the last entry of its row inside the tile), set by the lanes that own
                 // the rows, consumed by the segmented scan of phase B
@@ -768,7 +775,9 @@ namespace splacu {
     template<typename T, typename S>
     __global__ void __launch_bounds__(kBlock) mxv_fixup_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const T* __restrict__ mask,
                                                                T* r, T init, uint32_t n_tiles, const uint2* __restrict__ tile_rows,
-                                                               const T* __restrict__ carry, int accum) {
+                                                               const T* __restrict__ carry, int accum, const uint32_t* __restrict__ gate,
+                                                               uint32_t gate_max) {
+        if (gate && *gate >= gate_max) return;
         const uint32_t t    = blockIdx.x * blockDim.x + threadIdx.x;
         const uint32_t lane = threadIdx.x & 31u;
         uint32_t       row = 0, chain = 0;// chain = number of later tiles the row reaches into
@@ -903,7 +912,20 @@ namespace splacu {
         const uint32_t* hub_vals;// table base for MODE_HUB / MODE_SMEM16
         uint32_t        n_smem;  // slots staged in shared memory
         int             accum;
+        const uint32_t* gate;    // device counter of mask-selected rows: the pass runs only while *gate < gate_max (null: always)
+        uint32_t        gate_max;
     };
+
+    // rows selected by the mask of this call -> *out (zeroed before): lets the device choose between the column-class passes
+    // (dense masks) and the CSR kernel that tests the mask before any gather (sparse masks) without a host round trip
+    template<typename T>
+    __global__ void __launch_bounds__(kBlock) mask_count_kernel(Select sel, const T* __restrict__ mask, uint32_t n, uint32_t* __restrict__ out) {
+        uint32_t       c      = 0;
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += sel.test(mask[i]) ? 1u : 0u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((threadIdx.x & 31u) == 0u && c) atomicAdd(out, c);
+    }
 
     template<typename T, typename S, bool MASKED, int MODE, int WARPS>
     static int launch_wtile(S sr, Select sel, const TileJob& job, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
@@ -918,10 +940,10 @@ namespace splacu {
         const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
         kern<<<grid, WARPS * 32, smem, s>>>(sr, sel, job.Ap, reinterpret_cast<const uint32_t*>(job.Aj), reinterpret_cast<const T*>(job.Ax), v, mask, r, init,
                                             job.nnz, job.n_tiles, job.tile_rows, reinterpret_cast<T*>(job.carry), job.vec_ok, job.hub_vals, job.n_smem,
-                                            job.accum);
+                                            job.accum, job.gate, job.gate_max);
         SPLACU_LAUNCH_CHECK();
         mxv_fixup_kernel<T, S><<<(job.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, job.Ap, mask, r, init, job.n_tiles, job.tile_rows,
-                                                                                     reinterpret_cast<const T*>(job.carry), job.accum);
+                                                                                     reinterpret_cast<const T*>(job.carry), job.accum, job.gate, job.gate_max);
         SPLACU_LAUNCH_CHECK();
         return 0;
     }
@@ -974,6 +996,23 @@ namespace splacu {
             mxv_hub_pack_kernel<<<(M->n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->hub_cols, M->n_hub, reinterpret_cast<const uint32_t*>(v), M->hub_vals);
             SPLACU_LAUNCH_CHECK();
         }
+        if (M->n_phases && M->phase[0].seg) {
+            // dense masks (and ALWAYS): the column-class passes. Sparse masks: the CSR kernel below tests the mask before it
+            // touches Aj / Ax / v and wins as soon as a quarter of the rows is unselected. The device decides.
+            const uint32_t* gate     = nullptr;
+            uint32_t        gate_min = 0;
+            if (sel.reads_mask && M->sel_count) {
+                gate     = M->sel_count;
+                gate_min = (uint32_t) ((uint64_t) M->n_rows * (uint64_t) get_option(OPT_MXV_SEG_MIN_DENSITY) / 100u);
+                SPLACU_CUDA(cudaMemsetAsync(M->sel_count, 0, 4, s));
+                mask_count_kernel<T><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count);
+                SPLACU_LAUNCH_CHECK();
+            }
+            rc = seg_mxv(M, TypeCode<T>::value, sr.mult_op(), sr.add_op(), sel, v, mask, r, to_bits(init), gate, gate_min, s);
+            if (rc || !gate) return rc;
+            const TileJob job = {M->Ap, M->Aj, M->Ax, M->nnz, M->n_tiles, M->tile_rows, M->carry, (int) M->vec_ok, nullptr, 0u, 0, gate, gate_min};
+            return launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, s);
+        }
         if (M->n_phases) {
             // column classes, hottest first: the hub classes gather from shared memory only, the tail class from v.
             // The first non-empty class writes every row, the later ones accumulate onto it in this fixed order.
@@ -983,7 +1022,7 @@ namespace splacu {
                 const CsrPhase& ph = M->phase[p];
                 if (ph.nnz == 0 || (only && only != p + 1)) continue;
                 if (only) accum = p > 0;
-                const TileJob job = {ph.Ap, ph.Aj, ph.Ax, ph.nnz, ph.n_tiles, ph.tile_rows, ph.carry, 1, M->hub_vals + ph.slot_base, ph.n_slots, accum};
+                const TileJob job = {ph.Ap, ph.Aj, ph.Ax, ph.nnz, ph.n_tiles, ph.tile_rows, ph.carry, 1, M->hub_vals + ph.slot_base, ph.n_slots, accum, nullptr, 0u};
                 rc = ph.idx16 ? launch_job<T, S, MODE_SMEM16, kWarpsHub>(sr, sel, job, v, mask, r, init, s)
                               : launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, s);
                 if (rc) return rc;
@@ -991,7 +1030,7 @@ namespace splacu {
             }
             return 0;
         }
-        const TileJob job = {M->Ap, M->n_hub ? M->Aj_hub : M->Aj, M->Ax, M->nnz, M->n_tiles, M->tile_rows, M->carry, (int) M->vec_ok, M->hub_vals, M->n_hub_smem, 0};
+        const TileJob job = {M->Ap, M->n_hub ? M->Aj_hub : M->Aj, M->Ax, M->nnz, M->n_tiles, M->tile_rows, M->carry, (int) M->vec_ok, M->hub_vals, M->n_hub_smem, 0, nullptr, 0u};
         return M->n_hub ? launch_job<T, S, MODE_HUB, kWarps>(sr, sel, job, v, mask, r, init, s)
                         : launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, s);
     }

@@ -1,0 +1,388 @@
+// mxv_seg.cu -- the column classes of the pull product in the SEGMENTED-TILE format (see mxv_pull.cu for the classes).
+//
+// Semantics: reference src/cpu/cpu_mxv.hpp:88-103 for associative + commutative op_add without early exit:
+//            r[i] = select(mask[i]) ? add(init, sum of the products of row i) : init.
+//
+// Why a second format: in the CSR tile kernel a class that holds 2 .. 40 % of the entries still walks all n_rows row
+// extents per pass and parks / re-reads every product in shared memory (~700 instructions per 512-entry tile: the hub
+// classes were issue bound, ncu). Here the entries of a class are stored per 512-entry tile in LANE-BLOCKED order: a
+// coalesced 128-bit load hands every lane 16 CONSECUTIVE entries of the row order, so the products stay in registers.
+// Row structure is not Ap but, per tile,
+//   flags    16 bits per lane: entry i of the lane is the last entry of its row
+//   seg_row  the row of every flagged entry, in order (= the non-empty rows of the class; empty rows cost nothing)
+//   seg_base number of flags before the tile
+//   chain    does the tile start inside a row / how many tiles back that row began
+// A lane folds its 16 products serially, cutting at the flags; a warp-level segmented scan (fixed order: deterministic)
+// joins the pieces of rows that span lanes; the sums are handed through a 2 KB shared-memory slice to the lanes that own
+// the segments, which add them onto r (pre-filled with init): coalesced seg_row reads, near-coalesced r updates.
+// Rows that span tiles leave head / tail partials; mxv_seg_fixup_kernel chains them left to right.
+#include "common.cuh"
+#include "ops.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+namespace splacu {
+
+    namespace {
+        constexpr int      kBlock    = 256;
+        constexpr int      kSegWarps = 24;// warps per persistent CTA of a hub class (shared-memory gathers)
+#ifndef SPLACU_SEG_TAIL_WARPS
+#define SPLACU_SEG_TAIL_WARPS 20
+#endif
+        constexpr int      kSegTailWarps = SPLACU_SEG_TAIL_WARPS;// ... of the tail class: 102 registers, no spills with 16 gathers + a tile in flight
+        constexpr uint32_t kSmemMax  = 227u * 1024u;
+
+        __device__ __forceinline__ uint64_t policy_evict_first() {
+            uint64_t p;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+            return p;
+        }
+        __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p, uint64_t pol) {
+            uint4 r;
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                         : "l"(p), "l"(pol));
+            return r;
+        }
+        __device__ __forceinline__ uint32_t ld_gather(const uint32_t* p) {
+            uint32_t r;
+            asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+            return r;
+        }
+
+        // ---- build ---------------------------------------------------------------------------------
+        __global__ void __launch_bounds__(kBlock) seg_flags_kernel(const uint32_t* __restrict__ Ap, uint32_t n_rows, uint32_t* __restrict__ flags) {
+            const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+            if (row >= n_rows) return;
+            const uint32_t a = Ap[row], b = Ap[row + 1];
+            if (b == a) return;
+            const uint32_t e = b - 1u, tile = e >> 9, lane = (e & 511u) >> 4, i = e & 15u;
+            atomicOr(&flags[tile * 16u + (lane >> 1)], 1u << (i + 16u * (lane & 1u)));
+        }
+        __global__ void __launch_bounds__(kBlock) seg_tile_count_kernel(const uint32_t* __restrict__ flags, uint32_t n_tiles, uint32_t* __restrict__ count) {
+            const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+            if (t > n_tiles) return;
+            uint32_t c = 0;
+            if (t < n_tiles)
+                for (int w = 0; w < 16; ++w) c += __popc(flags[t * 16u + w]);
+            count[t] = c;
+        }
+        __global__ void __launch_bounds__(kBlock) seg_chain_kernel(const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ flags,
+                                                                   const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_row, uint32_t n_tiles,
+                                                                   uint32_t* __restrict__ chain) {
+            const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+            if (t >= n_tiles) return;
+            uint32_t w = 0;
+            if (t > 0) {
+                const bool prev_ends = (flags[(t - 1u) * 16u + 15u] >> 31) & 1u;// entry 511 of tile t - 1 = (lane 31, i 15)
+                if (!prev_ends) {
+                    w = 0x80000000u;
+                    if (seg_base[t + 1] > seg_base[t]) {// the row that reaches into the tile ends here
+                        const uint32_t start = Ap[seg_row[seg_base[t]]];
+                        w |= t - (start >> 9);
+                    }
+                }
+            }
+            chain[t] = w;
+        }
+    }// namespace
+
+    int seg_build(const Csr* M, CsrPhase& ph, const uint32_t* d_row_count, cudaStream_t s) {
+        void*     tmp   = nullptr;
+        uint32_t* count = nullptr;
+        uint32_t* d_num = nullptr;
+        int       rc    = 0;
+#define SEG_CUDA(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) {                                              \
+            rc = ::splacu::cuda_fail(_e, #expr, __FILE__, __LINE__);          \
+            goto done;                                                        \
+        }                                                                     \
+    } while (0)
+        {
+            const uint32_t nt = ph.n_tiles;
+            size_t         b1 = 0, b2 = 0;
+            thrust::counting_iterator<uint32_t> rows(0u);
+            SEG_CUDA(cudaMalloc(&ph.flags, (size_t) nt * 16 * 4));
+            SEG_CUDA(cudaMemsetAsync(ph.flags, 0, (size_t) nt * 16 * 4, s));
+            SEG_CUDA(cudaMalloc(&ph.seg_base, ((size_t) nt + 1) * 4));
+            SEG_CUDA(cudaMalloc(&ph.chain, (size_t) nt * 4));
+            SEG_CUDA(cudaMalloc(&ph.head, (size_t) nt * 4));
+            SEG_CUDA(cudaMalloc(&ph.tail, (size_t) nt * 4));
+            SEG_CUDA(cudaMalloc(&count, ((size_t) nt + 1) * 4));
+            SEG_CUDA(cudaMalloc(&d_num, 4));
+            // every non-empty row is one segment; + 32: the kernel reads the rows of a tile 32 at a time
+            SEG_CUDA(cudaMalloc(&ph.seg_row, ((size_t) M->n_rows + 32) * 4));
+            SEG_CUDA(cudaMemsetAsync(ph.seg_row, 0, ((size_t) M->n_rows + 32) * 4, s));
+            SEG_CUDA(cub::DeviceSelect::Flagged(nullptr, b1, rows, d_row_count, ph.seg_row, d_num, (int) M->n_rows, s));
+            SEG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, count, ph.seg_base, (int) nt + 1, s));
+            SEG_CUDA(cudaMalloc(&tmp, b1 > b2 ? b1 : b2));
+            SEG_CUDA(cub::DeviceSelect::Flagged(tmp, b1, rows, d_row_count, ph.seg_row, d_num, (int) M->n_rows, s));
+            seg_flags_kernel<<<(M->n_rows + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, M->n_rows, ph.flags);
+            seg_tile_count_kernel<<<(nt + 1 + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.flags, nt, count);
+            SEG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, b2, count, ph.seg_base, (int) nt + 1, s));
+            seg_chain_kernel<<<(nt + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, ph.flags, ph.seg_base, ph.seg_row, nt, ph.chain);
+            count_launch(5);
+            SEG_CUDA(cudaMemcpyAsync(&ph.n_segs, d_num, 4, cudaMemcpyDeviceToHost, s));
+            SEG_CUDA(cudaStreamSynchronize(s));
+            SEG_CUDA(cudaGetLastError());
+            ph.seg = true;
+            cudaFree(ph.Ap);// the row extents were only needed to derive the segments
+            ph.Ap = nullptr;
+        }
+    done:
+#undef SEG_CUDA
+        cudaFree(tmp);
+        cudaFree(count);
+        cudaFree(d_num);
+        return rc;
+    }
+
+    // ---- the kernel ----------------------------------------------------------------------------------
+    template<typename T, typename S, bool MASKED, bool IDX16, int WARPS>
+    __global__ void __launch_bounds__(WARPS * 32, 1)
+            mxv_seg_kernel(S sr, Select sel, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ flags,
+                           const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ chain,
+                           uint32_t* __restrict__ head, uint32_t* __restrict__ tail, const T* __restrict__ v, const T* __restrict__ mask, T* r,
+                           uint32_t n_tiles, const uint32_t* __restrict__ hub_vals, uint32_t n_slots, const uint32_t* __restrict__ gate,
+                           uint32_t gate_min) {
+        extern __shared__ __align__(16) uint32_t smem[];
+        if (MASKED && gate && *gate < gate_min) return;// sparse mask: the CSR kernel (mask tested before any gather) runs instead
+        constexpr int  NI   = IDX16 ? 2 : 4;// 128-bit index loads per lane and tile
+        const uint32_t tid  = threadIdx.x;
+        const uint32_t lane = tid & 31u;
+        const uint32_t warp = tid >> 5;
+        T*             s_out = reinterpret_cast<T*>(smem) + warp * 512;// segment sums of this warp's tile, in segment order
+        const T*       s_hub = reinterpret_cast<const T*>(smem) + WARPS * 512;
+        if (IDX16) {
+            uint4*       dst = reinterpret_cast<uint4*>(smem + WARPS * 512);
+            const uint4* src = reinterpret_cast<const uint4*>(hub_vals);
+            for (uint32_t i = tid; i < (n_slots + 3u) / 4u; i += WARPS * 32) dst[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        const uint64_t pol     = policy_evict_first();
+        const uint32_t n_warps = gridDim.x * WARPS;
+        const uint32_t first   = blockIdx.x * WARPS + warp;
+        const uint4*   idx4    = reinterpret_cast<const uint4*>(idx);
+        const uint4*   val4    = reinterpret_cast<const uint4*>(vals);
+
+        // ---- software pipeline: slices + flags + first 32 segment rows one tile ahead, seg_base / chain two tiles ahead ----
+        uint4    xv[4], xi[NI];
+        uint32_t fw = 0, sb0 = 0, sb1 = 0, ch = 0, srow = 0;
+        uint32_t q0 = 0, q1 = 0, qc = 0;
+        auto     load_meta = [&](uint32_t t) {
+            if (t < n_tiles) {
+                q0 = __ldg(seg_base + t);
+                q1 = __ldg(seg_base + t + 1);
+                qc = __ldg(chain + t);
+            }
+        };
+        auto prefetch = [&](uint32_t t) {
+            if (t >= n_tiles) return;
+            sb0 = q0, sb1 = q1, ch = qc;
+            load_meta(t + n_warps);
+#pragma unroll
+            for (int h = 0; h < NI; ++h) xi[h] = ld_stream_u4(idx4 + (size_t) t * (NI * 32) + h * 32 + lane, pol);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xv[q] = ld_stream_u4(val4 + (size_t) t * 128 + q * 32 + lane, pol);
+            fw   = __ldg(flags + t * 16u + (lane >> 1));
+            srow = __ldg(seg_row + sb0 + lane);// padded by 32 rows
+        };
+        load_meta(first);
+        prefetch(first);
+
+        for (uint32_t tile = first; tile < n_tiles; tile += n_warps) {
+            const uint32_t base = sb0, nfl = sb1 - sb0;
+            const bool     cont = (ch >> 31) != 0u;
+            const uint32_t row0 = srow;
+            const uint32_t fl   = (fw >> ((lane & 1u) * 16u)) & 0xffffu;
+            // r / mask of the first 32 segments: requested now, used by the hand-over at the end of the tile
+            T    old0  = sr.identity();
+            bool take0 = false;
+            if (lane < nfl) {
+                take0 = MASKED ? sel.test(mask[row0]) : true;
+                old0  = r[row0];
+            }
+
+            // ---- products of the lane's 16 consecutive entries ----
+            T p[16];
+            if (IDX16) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t w[4] = {xi[h].x, xi[h].y, xi[h].z, xi[h].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        p[8 * h + 2 * k]     = s_hub[w[k] & 0xffffu];
+                        p[8 * h + 2 * k + 1] = s_hub[w[k] >> 16];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    p[4 * q + 0] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].x));
+                    p[4 * q + 1] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].y));
+                    p[4 * q + 2] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].z));
+                    p[4 * q + 3] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].w));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                p[4 * q + 0] = sr.mult(from_bits<T>(xv[q].x), p[4 * q + 0]);
+                p[4 * q + 1] = sr.mult(from_bits<T>(xv[q].y), p[4 * q + 1]);
+                p[4 * q + 2] = sr.mult(from_bits<T>(xv[q].z), p[4 * q + 2]);
+                p[4 * q + 3] = sr.mult(from_bits<T>(xv[q].w), p[4 * q + 3]);
+            }
+            prefetch(tile + n_warps);// the slice registers are free again
+
+            // ---- position of the lane's first segment among the segments of the tile ----
+            const uint32_t cnt  = __popc(fl);
+            uint32_t       incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int) lane >= d) incl += t;
+            }
+            uint32_t k = incl - cnt;
+
+            // ---- pass 1: the lane's open tail (entries after its last flag); warp segmented scan -> carry-in ----
+            T open = sr.identity();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) open = ((fl >> i) & 1u) ? sr.identity() : sr.add(open, p[i]);
+            T    sv = open;
+            bool sf = fl != 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const T    vv = __shfl_up_sync(0xffffffffu, sv, d);
+                const bool ff = __shfl_up_sync(0xffffffffu, (int) sf, d) != 0;
+                if ((int) lane >= d) {
+                    if (!sf) sv = sr.add(vv, sv);
+                    sf = sf || ff;
+                }
+            }
+            T acc = __shfl_up_sync(0xffffffffu, sv, 1);
+            if (lane == 0) acc = sr.identity();
+            // ---- pass 2: segment sums -> shared memory in segment order ----
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                acc = sr.add(acc, p[i]);
+                if ((fl >> i) & 1u) {
+                    s_out[k] = acc;
+                    ++k;
+                    acc = sr.identity();
+                }
+            }
+            if (lane == 31) tail[tile] = to_bits(acc);// what follows the tile's last flag (the whole tile when it has none)
+            __syncwarp();
+
+            // ---- hand-over: the lane that owns segment o adds its sum onto r. (A two-stage software pipeline over the rounds of
+            //      32 segments was slower: more registers, spills.) ----
+            for (uint32_t o = lane; o < nfl; o += 32) {
+                uint32_t row  = row0;
+                bool     take = take0;
+                T        old  = old0;
+                if (o >= 32) {
+                    row  = __ldg(seg_row + base + o);
+                    take = MASKED ? sel.test(mask[row]) : true;
+                    old  = r[row];
+                }
+                const T sum = s_out[o];
+                if (o == 0 && cont) head[tile] = to_bits(sum);// the row began in an earlier tile: the fix-up adds the chain
+                else if (take) r[row] = sr.add(old, sum);
+            }
+            __syncwarp();// s_out is reused by the next tile
+        }
+    }
+
+    // rows that span tiles: r[row] += tail(t0) + tail(t0 + 1) + ... + tail(t - 1) + head(t), left to right; one thread per end
+    // tile, the whole warp for chains longer than 4 tiles (hub rows)
+    template<typename T, typename S>
+    __global__ void __launch_bounds__(kBlock) mxv_seg_fixup_kernel(S sr, Select sel, const uint32_t* __restrict__ chain, const uint32_t* __restrict__ seg_base,
+                                                                   const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ head,
+                                                                   const uint32_t* __restrict__ tail, const T* __restrict__ mask, T* r, uint32_t n_tiles,
+                                                                   const uint32_t* __restrict__ gate, uint32_t gate_min) {
+        if (gate && *gate < gate_min) return;
+        const uint32_t t    = blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t       len = 0, row = 0;
+        if (t < n_tiles) {
+            len = chain[t] & 0x7fffffffu;
+            if (len) {
+                row = seg_row[seg_base[t]];
+                if (sel.reads_mask && !sel.test(mask[row])) len = 0;
+            }
+        }
+        if (len > 0 && len <= 4) {
+            T acc = from_bits<T>(tail[t - len]);
+            for (uint32_t u = t - len + 1; u < t; ++u) acc = sr.add(acc, from_bits<T>(tail[u]));
+            acc    = sr.add(acc, from_bits<T>(head[t]));
+            r[row] = sr.add(r[row], acc);
+        }
+        uint32_t long_mask = __ballot_sync(0xffffffffu, len > 4);
+        while (long_mask) {
+            const int      src = __ffs(long_mask) - 1;
+            long_mask &= long_mask - 1;
+            const uint32_t t1 = __shfl_sync(0xffffffffu, t, src), L = __shfl_sync(0xffffffffu, len, src);
+            T              acc = sr.identity();
+            for (uint32_t u = lane; u < L; u += 32) acc = sr.add(acc, from_bits<T>(tail[t1 - L + u]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = sr.add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+            if ((int) lane == src) r[row] = sr.add(r[row], sr.add(acc, from_bits<T>(head[t])));
+        }
+    }
+
+    template<typename T, typename S, bool MASKED, bool IDX16>
+    static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const T* mask, T* r, const uint32_t* gate, uint32_t gate_min,
+                          cudaStream_t s) {
+        constexpr int  kW   = IDX16 ? kSegWarps : kSegTailWarps;
+        auto           kern = mxv_seg_kernel<T, S, MASKED, IDX16, kW>;
+        const uint32_t smem = kW * 512u * 4u + (IDX16 ? ((ph.n_slots + 3u) & ~3u) * 4u : 0u);
+        static bool    attr_done = false;// per instantiation
+        if (!attr_done) {
+            SPLACU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemMax));
+            attr_done = true;
+        }
+        if (smem > kSmemMax) {
+            set_error("mxv: hub class of %u slots does not fit in shared memory", ph.n_slots);
+            return SPLACU_E_INVALID;
+        }
+        const uint32_t want = (ph.n_tiles + kW - 1) / kW;
+        const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
+        kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
+                                                ph.tail, v, mask, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
+        SPLACU_LAUNCH_CHECK();
+        mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.seg_base, ph.seg_row, ph.head, ph.tail, mask, r,
+                                                                                        ph.n_tiles, gate, gate_min);
+        SPLACU_LAUNCH_CHECK();
+        return 0;
+    }
+
+    int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits,
+                const uint32_t* gate, uint32_t gate_min, cudaStream_t s) {
+        // every class accumulates onto r, which starts as init everywhere (unselected and empty rows keep it)
+        int rc = splacu_fill(d_r, init_bits, M->n_rows, s);
+        if (rc) return rc;
+        const int only = (int) get_option(OPT_MXV_PHASE_ONLY);
+        return dispatch_dtype(dtype, [&](auto tag) {
+            using T       = decltype(tag);
+            const T* v    = static_cast<const T*>(d_v);
+            const T* mask = static_cast<const T*>(d_mask);
+            T*       r    = static_cast<T*>(d_r);
+            return dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
+                using S = decltype(sr);
+                for (int p = 0; p < M->n_phases; ++p) {
+                    const CsrPhase& ph = M->phase[p];
+                    if (ph.nnz == 0 || (only && only != p + 1)) continue;
+                    int e;
+                    if (sel.reads_mask) e = ph.idx16 ? launch_seg<T, S, true, true>(sr, sel, M, ph, v, mask, r, gate, gate_min, s) : launch_seg<T, S, true, false>(sr, sel, M, ph, v, mask, r, gate, gate_min, s);
+                    else e = ph.idx16 ? launch_seg<T, S, false, true>(sr, sel, M, ph, v, mask, r, nullptr, 0u, s) : launch_seg<T, S, false, false>(sr, sel, M, ph, v, mask, r, nullptr, 0u, s);
+                    if (e) return e;
+                }
+                return 0;
+            });
+        });
+    }
+
+}// namespace splacu

@@ -83,6 +83,11 @@ with torch.cuda.stream(be.stream):
             err2 = ((r - r0).abs() / r0.abs().clamp(min=1e-30)).max().item()
             print(f"  max rel diff vs plain: {err:.2e} / {err2:.2e}", flush=True)
             if ph in per_phase:
+                for dens in (0.9, 0.5, 0.1):
+                    m = (torch.rand(n, device=dev) < dens).float()
+                    torch.cuda.synchronize()
+                    ms = timeit(lambda: be.mxv_masked(M, v, m, "MULT", "PLUS", "NQZERO", 0.0, out=r))
+                    print(f"    mask density {dens}: {ms:.3f} ms", flush=True)
                 for p in range(len(info["phase_nnz"])):
                     be.set_option("mxv_phase_only", p + 1)
                     ms_a = timeit(lambda: be.mxv_masked(M, v, None, "MULT", "PLUS", "ALWAYS", 0.0, out=r))

@@ -15,13 +15,14 @@ ap.add_argument("--scale", type=int, default=24)
 ap.add_argument("--phases", type=int, default=4)
 ap.add_argument("--masked", type=int, default=0)
 ap.add_argument("--calls", type=int, default=1)
+ap.add_argument("--density", type=float, default=1.0)
 args = ap.parse_args()
 be = Backend(0)
 dev = be.device
 n, Ap, Aj = graphs.rmat(args.scale, 16, seed=2, device=dev)
 Ax = graphs.pagerank_values(Ap, 0.85)
 v = torch.rand(n, device=dev)
-mask = torch.ones(n, device=dev)
+mask = (torch.rand(n, device=dev) < args.density).float()
 torch.cuda.synchronize()
 with torch.cuda.stream(be.stream):
     r = torch.empty(n, device=dev)

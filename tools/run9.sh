@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mxv_wtile" -c 4 -o gpurun_out/prof_phases2 -f python tools/prof_phase.py --phases 1 --masked 2 > gpurun_out/ncu_phases2.log 2>&1
-tail -3 gpurun_out/ncu_phases2.log
+for d in 1.0 0.5; do
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_seg_$d.csv python tools/prof_phase.py --phases 4 --masked 1 --density $d > gpurun_out/ncu_l.log 2>&1
+done
