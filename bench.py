@@ -335,22 +335,34 @@ def main():
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": f"failed: {ex}"}
 
+    phase_nnz = csr_info.get("phase_nnz") or []
+    if phase_nnz:
+        shares = ", ".join(f"{x / max(1, nnz_l):.3f}" for x in phase_nnz)
+        kernel_name = "mxv_seg_kernel"
+        kernel_desc = (f"mxv_seg_kernel x {len(phase_nnz)} column classes (entry shares {shares}; {csr_info['n_hub']} hub columns in shared-memory "
+                       f"tables of 16-bit slots, tail class gathers v) + mxv_seg_fixup_kernel per class")
+        roofline_note = (f"one step = one splacu_mxv_masked call = {len(phase_nnz)} launches of mxv_seg_kernel (one per column class) with their fix-ups, "
+                         "the mask-count / fill pass and the hub pack; achieved = algorithmic bytes of the step / its device time, traffic = DRAM bytes "
+                         "of all launches of the step")
+    else:
+        kernel_name = "mxv_wtile_kernel"
+        kernel_desc = f"mxv_wtile_kernel, {csr_info['n_tiles']} warp tiles of 512 nnz, {csr_info['n_hub']} hub columns"
+        roofline_note = "one launch = one step"
     if rank == 0:
         peak, peak_src = measured_peak()
         gteps = nnz / (ms_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": gteps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, n, nnz, world), kernel=f"mxv_wtile_kernel, {csr_info['n_tiles']} warp tiles of 512 nnz, "
-                                                                          f"{csr_info['n_hub']} hub columns"),
+            "config": dict(workload_config(args, n, nnz, world), kernel=kernel_desc),
             "clocks": clocks,
             "e2e": {"value": nnz / t_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,
                     "steps": e2e_steps, "result_checksum": checksum,
                     "path": "splacu_memcpy_h2d(v, mask) -> splacu_mxv_masked -> splacu_memcpy_d2h(r) -> splacu_sync, pinned host buffers"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "mxv_wtile_kernel", "achieved": achieved_min, "peak": peak, "unit": "GB/s", "frac": achieved_min / peak,
-                         "traffic": ncu_traffic("mxv_wtile_kernel"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": ms_kernel, "note": "rank-0 bytes, slowest rank's bandwidth" if world > 1 else "one launch = one step"},
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved_min, "peak": peak, "unit": "GB/s", "frac": achieved_min / peak,
+                         "traffic": ncu_traffic(kernel_name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": ms_kernel, "note": ("rank-0 bytes, slowest rank's bandwidth; " if world > 1 else "") + roofline_note},
             "cpu_baseline": cpu,
         }
         if extra:

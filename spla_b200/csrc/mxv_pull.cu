@@ -554,6 +554,7 @@ namespace splacu {
                 // a hub class whose slices are already in registers skips this pass (its gathers are on chip and cost nothing):
                 // products of unselected rows are simply never folded; `dense` is then re-estimated by the row loop
                 const bool need_pass = MASKED && !(MODE == MODE_SMEM16 && streamed);
+                bool       idle      = false;// the mask selects no row of the tile: nothing to stream, gather or sum
                 if (need_pass) {
                     // selected rows mark the 4-entry groups they need: the mask is tested before Aj / Ax / v are touched
 #pragma unroll
@@ -584,10 +585,12 @@ namespace splacu {
                         n_need += __popc(need[c]);
                     }
                     dense = n_need >= (uint32_t) (kMxvTile / 8);// at least half of the 128 groups
+                    idle  = n_need == 0u;
                 }
 
                 // ---- phase A: stream the tile, gather, multiply, park products in shared memory ----
-                if (vec_ok && hi - lo == (uint32_t) kMxvTile) {
+                if (idle) {
+                } else if (vec_ok && hi - lo == (uint32_t) kMxvTile) {
                     T x[kGroups][4];
                     if (!streamed) {
 #pragma unroll
@@ -683,7 +686,7 @@ namespace splacu {
                 __syncwarp();
                 // (2) every lane scans its 16 consecutive products: the sum of a segment lands on its flagged entry. Segments that
                 //     span lanes are joined by a warp-level segmented scan of the lanes' open tails (fixed order: deterministic).
-                {
+                if (!idle) {
                     const uint32_t fl = (s_flag[lane >> 1] >> ((lane & 1u) * 16u)) & 0xffffu;
                     // pass 1: the lane's open tail = sum of the entries after its last flag (all 16 when it has none); the products
                     // are read 4 at a time, and again in pass 2, rather than held in 16 registers across the warp scan
@@ -918,13 +921,23 @@ namespace splacu {
 
     // rows selected by the mask of this call -> *out (zeroed before): lets the device choose between the column-class passes
     // (dense masks) and the CSR kernel that tests the mask before any gather (sparse masks) without a host round trip
+    // (the same pass pre-fills r with init for the class passes, which accumulate onto it)
     template<typename T>
-    __global__ void __launch_bounds__(kBlock) mask_count_kernel(Select sel, const T* __restrict__ mask, uint32_t n, uint32_t* __restrict__ out) {
+    __global__ void __launch_bounds__(kBlock) mask_count_fill_kernel(Select sel, const T* __restrict__ mask, uint32_t n, uint32_t* __restrict__ out,
+                                                                     T* __restrict__ r, T init) {
+        __shared__ uint32_t s_count;
+        if (threadIdx.x == 0) s_count = 0u;
+        __syncthreads();
         uint32_t       c      = 0;
         const uint32_t stride = gridDim.x * blockDim.x;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += sel.test(mask[i]) ? 1u : 0u;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            c += sel.test(mask[i]) ? 1u : 0u;
+            r[i] = init;
+        }
         c = __reduce_add_sync(0xffffffffu, c);
-        if ((threadIdx.x & 31u) == 0u && c) atomicAdd(out, c);
+        if ((threadIdx.x & 31u) == 0u && c) atomicAdd(&s_count, c);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_count) atomicAdd(out, s_count);
     }
 
     template<typename T, typename S, bool MASKED, int MODE, int WARPS>
@@ -1005,7 +1018,7 @@ namespace splacu {
                 gate     = M->sel_count;
                 gate_min = (uint32_t) ((uint64_t) M->n_rows * (uint64_t) get_option(OPT_MXV_SEG_MIN_DENSITY) / 100u);
                 SPLACU_CUDA(cudaMemsetAsync(M->sel_count, 0, 4, s));
-                mask_count_kernel<T><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count);
+                mask_count_fill_kernel<T><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count, r, init);
                 SPLACU_LAUNCH_CHECK();
             }
             rc = seg_mxv(M, TypeCode<T>::value, sr.mult_op(), sr.add_op(), sel, v, mask, r, to_bits(init), gate, gate_min, s);

@@ -361,9 +361,12 @@ namespace splacu {
 
     int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits,
                 const uint32_t* gate, uint32_t gate_min, cudaStream_t s) {
-        // every class accumulates onto r, which starts as init everywhere (unselected and empty rows keep it)
-        int rc = splacu_fill(d_r, init_bits, M->n_rows, s);
-        if (rc) return rc;
+        // every class accumulates onto r, which starts as init everywhere (unselected and empty rows keep it); with a gate the
+        // caller's mask-count pass has filled it already
+        if (!gate) {
+            const int rc = splacu_fill(d_r, init_bits, M->n_rows, s);
+            if (rc) return rc;
+        }
         const int only = (int) get_option(OPT_MXV_PHASE_ONLY);
         return dispatch_dtype(dtype, [&](auto tag) {
             using T       = decltype(tag);
