@@ -51,7 +51,7 @@ def workload_config(args, n=None, nnz=None, world=1):
         "workload": f"mxv_masked FLOAT {OPS[0]}/{OPS[1]}/{OPS[2]} all-ones mask (PageRank step, E = nnz) on RMAT scale-{args.scale} "
                     f"edge-factor {args.edge_factor}, symmetrised + dedup + no loops, A[i][j] = 0.85/outdeg(i), v = 1/N",
         "graph": f"rmat-{args.scale}",
-        "parallelism": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks + all-gather of result windows",
+        "parallelism": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, vector in the padded equal-window layout, one in-place ncclAllGather per step",
         "cache": "inputs larger than L2 (CSR >> 126 MB), no flush between iterations",
     }
     if n is not None:
@@ -236,17 +236,26 @@ def main():
     nnz_l = int(Aj_l.numel())
     del Ap, Aj, Ax
     torch.cuda.empty_cache()
-    v = torch.full((n,), 1.0 / n, dtype=torch.float32, device=dev)
-    v_next = torch.empty_like(v)
+    # N > 1: the vector lives in the padded layout of spla_b200.dist (equal windows, rank p at [p*W, p*W + rows_p)), so that a step
+    # ends with one in-place all-gather; the column ids of the local slice are mapped once. N = 1: w0 = 0, n_vec = n.
+    if world > 1:
+        W, shifts = sd.padded_layout(bounds)
+        Aj_l = sd.to_padded_index(Aj_l, bounds, shifts)
+        n_vec, w0 = world * W, rank * W
+    else:
+        W, n_vec, w0 = n, n, 0
+    v = torch.full((n_vec,), 1.0 / n, dtype=torch.float32, device=dev)
+    v_next = torch.full((n_vec,), 1.0 / n, dtype=torch.float32, device=dev)
     mask_l = torch.ones(r1 - r0, dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
-    M = be.csr(r1 - r0, n, Ap_l, Aj_l, Ax_l)
+    M = be.csr(r1 - r0, n_vec, Ap_l, Aj_l, Ax_l)
     csr_info = be.csr_info(M)
+    w1 = w0 + (r1 - r0)
 
     def step(src, dst):
-        be.mxv_masked(M, src, mask_l, *OPS, 0.0, out=dst[r0:r1])
+        be.mxv_masked(M, src, mask_l, *OPS, 0.0, out=dst[w0:w1])
         if world > 1:
-            sd.allgather_windows(dst, bounds)
+            sd.allgather_padded(dst, W)
 
     def barrier():
         torch.cuda.synchronize()
@@ -288,7 +297,7 @@ def main():
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record(be.stream)
         for _ in range(args.steps):
-            be.mxv_masked(M, a, mask_l, *OPS, 0.0, out=b[r0:r1])
+            be.mxv_masked(M, a, mask_l, *OPS, 0.0, out=b[w0:w1])
         k1.record(be.stream)
         barrier()
         ms_kernel = k0.elapsed_time(k1) / args.steps
@@ -297,19 +306,19 @@ def main():
         achieved_min = -max_over_ranks(-achieved)  # slowest rank's kernel bandwidth
 
         # ---- e2e: the C-ABI call with HOST buffers (pinned h2d of v and the mask window, d2h of the result window) ----
-        hv = torch.full((n,), 1.0 / n, dtype=torch.float32).pin_memory()
+        hv = torch.full((n_vec,), 1.0 / n, dtype=torch.float32).pin_memory()
         hm = torch.ones(r1 - r0, dtype=torch.float32).pin_memory()
         hr = torch.empty(r1 - r0, dtype=torch.float32).pin_memory()
         lib, sp = be.lib, be.stream_ptr
         e2e_steps = max(3, min(args.steps, 10))
 
         def e2e_step():
-            lib.splacu_memcpy_h2d(C.c_void_p(a.data_ptr()), C.c_void_p(hv.data_ptr()), n * 4, sp)
+            lib.splacu_memcpy_h2d(C.c_void_p(a.data_ptr()), C.c_void_p(hv.data_ptr()), n_vec * 4, sp)
             lib.splacu_memcpy_h2d(C.c_void_p(mask_l.data_ptr()), C.c_void_p(hm.data_ptr()), (r1 - r0) * 4, sp)
             rc = lib.splacu_mxv_masked(M.handle, FLOAT, BIN[OPS[0]], BIN[OPS[1]], SEL[OPS[2]], C.c_void_p(a.data_ptr()), C.c_void_p(mask_l.data_ptr()),
-                                       C.c_void_p(b[r0:r1].data_ptr()), scalar_bits(FLOAT, 0.0), 0, sp)
+                                       C.c_void_p(b[w0:w1].data_ptr()), scalar_bits(FLOAT, 0.0), 0, sp)
             assert rc == 0
-            lib.splacu_memcpy_d2h(C.c_void_p(hr.data_ptr()), C.c_void_p(b[r0:r1].data_ptr()), (r1 - r0) * 4, sp)
+            lib.splacu_memcpy_d2h(C.c_void_p(hr.data_ptr()), C.c_void_p(b[w0:w1].data_ptr()), (r1 - r0) * 4, sp)
             lib.splacu_sync(sp)
 
         e2e_step()
@@ -317,8 +326,51 @@ def main():
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
-        t_e2e = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-        h2d = (n + (r1 - r0)) * 4
+        t_serial = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+
+        # The same calls, pipelined the way a host application streams batches through the C ABI: three streams (copy-in, the
+        # backend's compute stream, copy-out) and two sets of device buffers, ordered by events. Every step still uploads its v and
+        # mask from pinned host memory and downloads its r; PCIe is full duplex, so the upload of step k+1 overlaps the kernels and
+        # the download of step k. All kernels stay on ONE stream: the matrix handle's scratch is not reentrant.
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        p_in, p_out = C.c_void_p(s_in.cuda_stream), C.c_void_p(s_out.cuda_stream)
+        dv = [torch.empty(n_vec, dtype=torch.float32, device=dev) for _ in range(2)]
+        dm = [torch.empty(r1 - r0, dtype=torch.float32, device=dev) for _ in range(2)]
+        dr = [torch.empty(r1 - r0, dtype=torch.float32, device=dev) for _ in range(2)]
+        hrs = [torch.empty(r1 - r0, dtype=torch.float32).pin_memory() for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_k = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        torch.cuda.synchronize()
+
+        def e2e_pipelined(steps):
+            for k in range(steps):
+                q = k & 1
+                if k >= 2:
+                    s_in.wait_event(ev_k[q])    # the kernels of step k-2 have consumed dv[q] / dm[q]
+                lib.splacu_memcpy_h2d(C.c_void_p(dv[q].data_ptr()), C.c_void_p(hv.data_ptr()), n_vec * 4, p_in)
+                lib.splacu_memcpy_h2d(C.c_void_p(dm[q].data_ptr()), C.c_void_p(hm.data_ptr()), (r1 - r0) * 4, p_in)
+                ev_in[q].record(s_in)
+                be.stream.wait_event(ev_in[q])
+                if k >= 2:
+                    be.stream.wait_event(ev_out[q])  # dr[q] of step k-2 has been downloaded
+                rc = lib.splacu_mxv_masked(M.handle, FLOAT, BIN[OPS[0]], BIN[OPS[1]], SEL[OPS[2]], C.c_void_p(dv[q].data_ptr()),
+                                           C.c_void_p(dm[q].data_ptr()), C.c_void_p(dr[q].data_ptr()), scalar_bits(FLOAT, 0.0), 0, sp)
+                assert rc == 0
+                ev_k[q].record(be.stream)
+                s_out.wait_event(ev_k[q])
+                lib.splacu_memcpy_d2h(C.c_void_p(hrs[q].data_ptr()), C.c_void_p(dr[q].data_ptr()), (r1 - r0) * 4, p_out)
+                ev_out[q].record(s_out)
+            torch.cuda.synchronize()
+
+        e2e_pipelined(2)
+        barrier()
+        pipe_steps = 2 * e2e_steps
+        t0 = time.perf_counter()
+        e2e_pipelined(pipe_steps)
+        t_e2e = max_over_ranks((time.perf_counter() - t0) / pipe_steps)
+        assert torch.equal(hrs[0], hr) and torch.equal(hrs[1], hr), "pipelined e2e result differs from the serial one"
+        h2d = (n_vec + (r1 - r0)) * 4
         d2h = (r1 - r0) * 4
         checksum = float(hr.double().sum())
 
@@ -357,8 +409,10 @@ def main():
             "config": dict(workload_config(args, n, nnz, world), kernel=kernel_desc),
             "clocks": clocks,
             "e2e": {"value": nnz / t_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3,
-                    "steps": e2e_steps, "result_checksum": checksum,
-                    "path": "splacu_memcpy_h2d(v, mask) -> splacu_mxv_masked -> splacu_memcpy_d2h(r) -> splacu_sync, pinned host buffers"},
+                    "steps": pipe_steps, "result_checksum": checksum, "ms_per_step_unpipelined": t_serial * 1e3,
+                    "path": "per step: splacu_memcpy_h2d(v, mask) from pinned host memory -> splacu_mxv_masked -> splacu_memcpy_d2h(r); steps pipelined "
+                            "over three streams and two device buffer sets (upload of step k+1 overlaps kernels and download of step k); "
+                            "ms_per_step_unpipelined = the same calls back to back on one stream with a sync per step"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved_min, "peak": peak, "unit": "GB/s", "frac": achieved_min / peak,
                          "traffic": ncu_traffic(kernel_name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,

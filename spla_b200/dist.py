@@ -79,6 +79,40 @@ def allgather_windows(full, bounds, group=None):
     return full
 
 
+def padded_layout(bounds, align=32):
+    """Distributed layout of a full-length vector with EQUAL windows: the rows [b[p], b[p+1]) of rank p live at
+    [p*W, p*W + size_p) of a vector of length world*W, W = the largest window rounded up to `align` elements. The nnz-balanced
+    windows are uneven, and an uneven all-gather costs either one broadcast per owner or staging copies; in this layout a step
+    ends with ONE in-place ncclAllGather and no copy. Column ids of the matrix are mapped once (to_padded_index).
+    Returns (W, shifts) with padded index = global index + shifts[owner]."""
+    world = len(bounds) - 1
+    w = max(bounds[p + 1] - bounds[p] for p in range(world))
+    w = (max(w, 1) + align - 1) // align * align
+    return w, [p * w - bounds[p] for p in range(world)]
+
+
+def to_padded_index(idx, bounds, shifts):
+    """global row / column ids -> ids in the padded layout (idx: integer tensor on any device)."""
+    cuts = torch.tensor(bounds[1:-1], dtype=torch.int64, device=idx.device)
+    owner = torch.bucketize(idx.to(torch.int64), cuts, right=True)
+    sh = torch.tensor(shifts, dtype=torch.int64, device=idx.device)
+    return (idx.to(torch.int64) + sh[owner]).to(idx.dtype)
+
+
+def allgather_padded(full_padded, w, group=None):
+    """In-place all-gather of the equal windows full_padded[p*w:(p+1)*w] (one collective, no staging on NCCL)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return full_padded
+    rank = dist.get_rank(group)
+    buf = full_padded.view(torch.int32) if full_padded.dtype == torch.uint32 else full_padded
+    mine = buf[rank * w:(rank + 1) * w]
+    if dist.get_backend(group) != "nccl":
+        mine = mine.clone()  # gloo wants distinct buffers
+    dist.all_gather_into_tensor(buf[:world * w], mine, group=group)
+    return full_padded
+
+
 def exchange_frontier(vi_local, vx_local, offset, group=None):
     """All-gather of sparse frontier pieces. Each rank contributes (indices local to its window + offset, values);
     returns the concatenated global (vi, vx), sorted because windows are disjoint and ordered by rank.

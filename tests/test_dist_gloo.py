@@ -56,6 +56,22 @@ def _worker(rank, world, port, out_dir):
         want = orc.mxv_masked(INT, "MULT", "PLUS", "EQZERO", hAp, hAj, hAx, v.numpy(), mask.numpy(), 0)
         assert np.array_equal(full.numpy(), want), "row-sharded mxv + all-gather differs from the single-device product"
 
+        # ---- pull in the padded layout: equal windows, column ids mapped once, ONE in-place all-gather ----
+        W, shifts = sd.padded_layout(b)
+        assert W % 32 == 0 and all(b[p + 1] - b[p] <= W for p in range(world))
+        Aj_p = sd.to_padded_index(Aj_l, b, shifts)
+        v_p = torch.zeros(world * W, dtype=torch.int32)
+        for p in range(world):
+            v_p[p * W:p * W + (b[p + 1] - b[p])] = v[b[p]:b[p + 1]]
+        part_p = orc.mxv_masked(INT, "MULT", "PLUS", "EQZERO", Ap_l.numpy().astype(np.uint32), Aj_p.numpy().astype(np.uint32), Ax_l.numpy(),
+                                v_p.numpy(), mask[r0:r1].numpy(), 0)
+        assert np.array_equal(part_p, part), "mapped column ids change the local product"
+        full_p = torch.full((world * W,), -7, dtype=torch.int32)
+        full_p[rank * W:rank * W + (r1 - r0)] = torch.from_numpy(part_p)
+        sd.allgather_padded(full_p, W)
+        got = torch.cat([full_p[p * W:p * W + (b[p + 1] - b[p])] for p in range(world)])
+        assert np.array_equal(got.numpy(), want), "padded-layout all-gather differs from the single-device product"
+
         # ---- push: column blocks, frontier exchange ----
         cb = sd.column_boundaries(Aj, n, world)
         c0, c1 = cb[rank], cb[rank + 1]
