@@ -120,6 +120,7 @@ namespace splacu {
         int       n_phases     = 0;
         CsrPhase  phase[kMaxHubPhases + 1];
         uint32_t* sel_count    = nullptr;// device counter: rows the mask of the current call selects (chooses the masked path on the device)
+        uint32_t* sel_bits     = nullptr;// [n_rows / 32] bit i = select(mask[i]) of the current call: what the class passes read
     };
 
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel

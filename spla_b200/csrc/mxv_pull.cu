@@ -395,6 +395,7 @@ namespace splacu {
                     return rc;
                 }
                 HUB_CUDA(cudaMalloc(&M->sel_count, 4));
+                HUB_CUDA(cudaMalloc(&M->sel_bits, ((size_t) M->n_rows + 31) / 32 * 4 + 4));
             } else {
                 HUB_CUDA(cudaMalloc(&M->Aj_hub, (size_t) M->nnz * 4));
                 hub_encode_kernel<<<grid_for(M->nnz, kBlock, 8), kBlock, 0, s>>>(M->Aj, M->nnz, count, M->Aj_hub);
@@ -921,20 +922,26 @@ namespace splacu {
 
     // rows selected by the mask of this call -> *out (zeroed before): lets the device choose between the column-class passes
     // (dense masks) and the CSR kernel that tests the mask before any gather (sparse masks) without a host round trip
-    // (the same pass pre-fills r with init for the class passes, which accumulate onto it)
+    // (the same pass pre-fills r with init for the class passes, which accumulate onto it, and leaves select(mask[i]) as a bitmap:
+    //  2 MB that stay in L2 instead of 64 MB read again by every class pass)
     template<typename T>
     __global__ void __launch_bounds__(kBlock) mask_count_fill_kernel(Select sel, const T* __restrict__ mask, uint32_t n, uint32_t* __restrict__ out,
-                                                                     T* __restrict__ r, T init) {
+                                                                     uint32_t* __restrict__ sel_bits, T* __restrict__ r, T init) {
         __shared__ uint32_t s_count;
         if (threadIdx.x == 0) s_count = 0u;
         __syncthreads();
         uint32_t       c      = 0;
-        const uint32_t stride = gridDim.x * blockDim.x;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-            c += sel.test(mask[i]) ? 1u : 0u;
-            r[i] = init;
+        const uint32_t stride = gridDim.x * blockDim.x;// a multiple of 32: a warp always covers 32 consecutive rows
+        const uint32_t n_pad  = (n + 31u) & ~31u;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+            const bool     p = i < n && sel.test(mask[i]);
+            const uint32_t m = __ballot_sync(0xffffffffu, p);
+            if (i < n) r[i] = init;
+            if ((threadIdx.x & 31u) == 0u) {
+                sel_bits[i >> 5] = m;
+                c += __popc(m);
+            }
         }
-        c = __reduce_add_sync(0xffffffffu, c);
         if ((threadIdx.x & 31u) == 0u && c) atomicAdd(&s_count, c);
         __syncthreads();
         if (threadIdx.x == 0 && s_count) atomicAdd(out, s_count);
@@ -1018,7 +1025,7 @@ namespace splacu {
                 gate     = M->sel_count;
                 gate_min = (uint32_t) ((uint64_t) M->n_rows * (uint64_t) get_option(OPT_MXV_SEG_MIN_DENSITY) / 100u);
                 SPLACU_CUDA(cudaMemsetAsync(M->sel_count, 0, 4, s));
-                mask_count_fill_kernel<T><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count, r, init);
+                mask_count_fill_kernel<T><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count, M->sel_bits, r, init);
                 SPLACU_LAUNCH_CHECK();
             }
             rc = seg_mxv(M, TypeCode<T>::value, sr.mult_op(), sr.add_op(), sel, v, mask, r, to_bits(init), gate, gate_min, s);

@@ -146,7 +146,7 @@ namespace splacu {
     __global__ void __launch_bounds__(WARPS * 32, 1)
             mxv_seg_kernel(S sr, Select sel, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ flags,
                            const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ chain,
-                           uint32_t* __restrict__ head, uint32_t* __restrict__ tail, const T* __restrict__ v, const T* __restrict__ mask, T* r,
+                           uint32_t* __restrict__ head, uint32_t* __restrict__ tail, const T* __restrict__ v, const uint32_t* __restrict__ sel_bits, T* r,
                            uint32_t n_tiles, const uint32_t* __restrict__ hub_vals, uint32_t n_slots, const uint32_t* __restrict__ gate,
                            uint32_t gate_min) {
         extern __shared__ __align__(16) uint32_t smem[];
@@ -203,7 +203,7 @@ namespace splacu {
             T    old0  = sr.identity();
             bool take0 = false;
             if (lane < nfl) {
-                take0 = MASKED ? sel.test(mask[row0]) : true;
+                take0 = MASKED ? ((sel_bits[row0 >> 5] >> (row0 & 31u)) & 1u) != 0u : true;
                 old0  = r[row0];
             }
 
@@ -285,7 +285,7 @@ namespace splacu {
                 T        old  = old0;
                 if (o >= 32) {
                     row  = __ldg(seg_row + base + o);
-                    take = MASKED ? sel.test(mask[row]) : true;
+                    take = MASKED ? ((sel_bits[row >> 5] >> (row & 31u)) & 1u) != 0u : true;
                     old  = r[row];
                 }
                 const T sum = s_out[o];
@@ -301,7 +301,8 @@ namespace splacu {
     template<typename T, typename S>
     __global__ void __launch_bounds__(kBlock) mxv_seg_fixup_kernel(S sr, Select sel, const uint32_t* __restrict__ chain, const uint32_t* __restrict__ seg_base,
                                                                    const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ head,
-                                                                   const uint32_t* __restrict__ tail, const T* __restrict__ mask, T* r, uint32_t n_tiles,
+                                                                   const uint32_t* __restrict__ tail, const uint32_t* __restrict__ sel_bits, T* r,
+                                                                   uint32_t n_tiles,
                                                                    const uint32_t* __restrict__ gate, uint32_t gate_min) {
         if (gate && *gate < gate_min) return;
         const uint32_t t    = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,7 +312,7 @@ namespace splacu {
             len = chain[t] & 0x7fffffffu;
             if (len) {
                 row = seg_row[seg_base[t]];
-                if (sel.reads_mask && !sel.test(mask[row])) len = 0;
+                if (sel_bits && !((sel_bits[row >> 5] >> (row & 31u)) & 1u)) len = 0;
             }
         }
         if (len > 0 && len <= 4) {
@@ -334,8 +335,8 @@ namespace splacu {
     }
 
     template<typename T, typename S, bool MASKED, bool IDX16>
-    static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const T* mask, T* r, const uint32_t* gate, uint32_t gate_min,
-                          cudaStream_t s) {
+    static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
+                          uint32_t gate_min, cudaStream_t s) {
         constexpr int  kW   = IDX16 ? kSegWarps : kSegTailWarps;
         auto           kern = mxv_seg_kernel<T, S, MASKED, IDX16, kW>;
         const uint32_t smem = kW * 512u * 4u + (IDX16 ? ((ph.n_slots + 3u) & ~3u) * 4u : 0u);
@@ -351,9 +352,9 @@ namespace splacu {
         const uint32_t want = (ph.n_tiles + kW - 1) / kW;
         const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
         kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
-                                                ph.tail, v, mask, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
+                                                ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
         SPLACU_LAUNCH_CHECK();
-        mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.seg_base, ph.seg_row, ph.head, ph.tail, mask, r,
+        mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.seg_base, ph.seg_row, ph.head, ph.tail, sel_bits, r,
                                                                                         ph.n_tiles, gate, gate_min);
         SPLACU_LAUNCH_CHECK();
         return 0;
@@ -367,11 +368,15 @@ namespace splacu {
             const int rc = splacu_fill(d_r, init_bits, M->n_rows, s);
             if (rc) return rc;
         }
+        if (sel.reads_mask && !(gate && M->sel_bits)) {
+            set_error("mxv: the class passes need the selection bitmap of the mask-count pass");
+            return SPLACU_E_INVALID;
+        }
+        (void) d_mask;
         const int only = (int) get_option(OPT_MXV_PHASE_ONLY);
         return dispatch_dtype(dtype, [&](auto tag) {
             using T       = decltype(tag);
             const T* v    = static_cast<const T*>(d_v);
-            const T* mask = static_cast<const T*>(d_mask);
             T*       r    = static_cast<T*>(d_r);
             return dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
                 using S = decltype(sr);
@@ -379,8 +384,8 @@ namespace splacu {
                     const CsrPhase& ph = M->phase[p];
                     if (ph.nnz == 0 || (only && only != p + 1)) continue;
                     int e;
-                    if (sel.reads_mask) e = ph.idx16 ? launch_seg<T, S, true, true>(sr, sel, M, ph, v, mask, r, gate, gate_min, s) : launch_seg<T, S, true, false>(sr, sel, M, ph, v, mask, r, gate, gate_min, s);
-                    else e = ph.idx16 ? launch_seg<T, S, false, true>(sr, sel, M, ph, v, mask, r, nullptr, 0u, s) : launch_seg<T, S, false, false>(sr, sel, M, ph, v, mask, r, nullptr, 0u, s);
+                    if (sel.reads_mask && gate) e = ph.idx16 ? launch_seg<T, S, true, true>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s) : launch_seg<T, S, true, false>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s);
+                    else e = ph.idx16 ? launch_seg<T, S, false, true>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s) : launch_seg<T, S, false, false>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s);
                     if (e) return e;
                 }
                 return 0;

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for N in 2; do
+N=$1
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; python - <<PY
 import json
 try:
@@ -8,4 +8,3 @@ try:
 except Exception as e:
     print('fail', e); print(open('gpurun_out/bench_${N}gpu.err').read()[-2000:])
 PY
-done
