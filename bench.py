@@ -26,6 +26,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PEER_MODE = [False]
 METRIC = "GTEPS of masked mxv/vxm, RMAT-24, 1/2/4/8 B200; % of HBM roofline"
 UNIT = "GTEPS"
 OPS = ("MULT", "PLUS", "NQZERO")
@@ -51,7 +52,7 @@ def workload_config(args, n=None, nnz=None, world=1):
         "workload": f"mxv_masked FLOAT {OPS[0]}/{OPS[1]}/{OPS[2]} all-ones mask (PageRank step, E = nnz) on RMAT scale-{args.scale} "
                     f"edge-factor {args.edge_factor}, symmetrised + dedup + no loops, A[i][j] = 0.85/outdeg(i), v = 1/N",
         "graph": f"rmat-{args.scale}",
-        "parallelism": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, vector in the padded equal-window layout, one in-place ncclAllGather per step",
+        "parallelism": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, vector in the padded equal-window layout, " + ("windows published to the peers by one kernel of NVLink peer stores + device barrier per step" if PEER_MODE[0] else "one in-place ncclAllGather per step"),
         "cache": "inputs larger than L2 (CSR >> 126 MB), no flush between iterations",
     }
     if n is not None:
@@ -244,8 +245,27 @@ def main():
         n_vec, w0 = world * W, rank * W
     else:
         W, n_vec, w0 = n, n, 0
-    v = torch.full((n_vec,), 1.0 / n, dtype=torch.float32, device=dev)
-    v_next = torch.full((n_vec,), 1.0 / n, dtype=torch.float32, device=dev)
+    # N > 1: a step ends with one in-place ncclAllGather of the equal windows. SPLA_B200_P2P=1 switches to peer-mapped copies of
+    # the vector and one kernel of NVLink peer stores + a device barrier per step (splacu_publish_window); measured on 2 / 8 B200s it
+    # is within noise of the NCCL call (560 vs 538, 1013 vs 1034 GTEPS: the step is bound by synchronisation, not bytes), so the
+    # collective library stays the default.
+    peer = None
+    if world > 1 and os.environ.get("SPLA_B200_P2P", "0") == "1":
+        try:
+            pv = [sd.PeerVector(be, n_vec), sd.PeerVector(be, n_vec)]
+            peer = {pv[0].tensor.data_ptr(): pv[0], pv[1].tensor.data_ptr(): pv[1]}
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                print(f"bench: peer-mapped vectors unavailable ({ex}); using ncclAllGather", file=sys.stderr)
+            peer = None
+    PEER_MODE[0] = bool(peer)
+    if peer:
+        v, v_next = pv[0].tensor[:n_vec], pv[1].tensor[:n_vec]
+        v.fill_(1.0 / n)
+        v_next.fill_(1.0 / n)
+    else:
+        v = torch.full((n_vec,), 1.0 / n, dtype=torch.float32, device=dev)
+        v_next = torch.full((n_vec,), 1.0 / n, dtype=torch.float32, device=dev)
     mask_l = torch.ones(r1 - r0, dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
     M = be.csr(r1 - r0, n_vec, Ap_l, Aj_l, Ax_l)
@@ -254,7 +274,9 @@ def main():
 
     def step(src, dst):
         be.mxv_masked(M, src, mask_l, *OPS, 0.0, out=dst[w0:w1])
-        if world > 1:
+        if peer:
+            peer[dst.data_ptr()].publish(w0, r1 - r0)
+        elif world > 1:
             sd.allgather_padded(dst, W)
 
     def barrier():
@@ -304,6 +326,12 @@ def main():
         alg_bytes = mxv_alg_bytes(r1 - r0, n, nnz_l, reads_mask=True)
         achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
         achieved_min = -max_over_ranks(-achieved)  # slowest rank's kernel bandwidth
+        kernel_ms_ranks = [ms_kernel]
+        if world > 1:
+            t = torch.zeros(world, dtype=torch.float64, device=dev)
+            t[rank] = ms_kernel
+            dist.all_reduce(t)
+            kernel_ms_ranks = [round(float(x), 4) for x in t.tolist()]
 
         # ---- e2e: the C-ABI call with HOST buffers (pinned h2d of v and the mask window, d2h of the result window) ----
         hv = torch.full((n_vec,), 1.0 / n, dtype=torch.float32).pin_memory()
@@ -416,7 +444,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved_min, "peak": peak, "unit": "GB/s", "frac": achieved_min / peak,
                          "traffic": ncu_traffic(kernel_name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": ms_kernel, "note": ("rank-0 bytes, slowest rank's bandwidth; " if world > 1 else "") + roofline_note},
+                         "kernel_ms": ms_kernel, "kernel_ms_per_rank": kernel_ms_ranks, "note": ("rank-0 bytes, slowest rank's bandwidth; " if world > 1 else "") + roofline_note},
             "cpu_baseline": cpu,
         }
         if extra:

@@ -88,6 +88,14 @@ SPLACU_API int splacu_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, v
 /* replaces kernels fill_zero / fill_value, reference src/opencl/kernels/fill.cl:30,41 (cl_fill.hpp) */
 SPLACU_API int splacu_fill(void* d_dst, uint32_t value_bits, size_t n, void* stream);
 
+/* Multi-GPU (single box, net-new relative to the single-device reference): publish the window
+ * [offset, offset + count) of this rank's copy of a 4-byte-element vector into the copies held by its peers, as one kernel of
+ * 128-bit peer stores. peer_bases[q] = device pointer to rank q's copy, mapped into this process (symmetric allocation: same
+ * layout everywhere), peer_bases[self] = the local copy. offset / count in elements, multiples of 4; the caller orders steps
+ * with a cross-device barrier. Replaces the per-step ncclAllGather of the row-sharded pull. */
+#define SPLACU_MAX_PEERS 16
+SPLACU_API int splacu_publish_window(void* const* peer_bases, int n_peers, int self, size_t offset, size_t count, void* stream);
+
 /* ---- device CSR matrix: replaces CLCsr + cl_csr_init, reference src/opencl/cl_formats.hpp:93-103,
  *      cl_format_csr.hpp:40-63. The handle does not own Ap/Aj/Ax; it owns the load-balancing
  *      metadata built once per matrix (decorations may carry extra data, core/accelerator.hpp:50-52). */

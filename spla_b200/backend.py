@@ -30,7 +30,7 @@ SYMBOLS = [
     "splacu_default_stream", "splacu_sync", "splacu_last_error", "splacu_launch_count",
     "splacu_set_option", "splacu_get_option", "splacu_csr_info", "splacu_csr_phases",
     "splacu_malloc", "splacu_free", "splacu_malloc_host", "splacu_free_host",
-    "splacu_memcpy_h2d", "splacu_memcpy_d2h", "splacu_memcpy_d2d", "splacu_fill",
+    "splacu_memcpy_h2d", "splacu_memcpy_d2h", "splacu_memcpy_d2d", "splacu_fill", "splacu_publish_window",
     "splacu_csr_create", "splacu_csr_destroy", "splacu_mxv_masked",
     "splacu_workspace_create", "splacu_workspace_destroy",
     "splacu_vxm_masked_begin", "splacu_vxm_masked_emit", "splacu_vxm_masked",
@@ -64,7 +64,7 @@ def load_library(build_if_missing=True):
         "splacu_malloc": [C.POINTER(vp), sz], "splacu_free": [vp],
         "splacu_malloc_host": [C.POINTER(vp), sz], "splacu_free_host": [vp],
         "splacu_memcpy_h2d": [vp, vp, sz, vp], "splacu_memcpy_d2h": [vp, vp, sz, vp], "splacu_memcpy_d2d": [vp, vp, sz, vp],
-        "splacu_fill": [vp, u32, sz, vp],
+        "splacu_fill": [vp, u32, sz, vp], "splacu_publish_window": [C.POINTER(vp), i32, i32, sz, sz, vp],
         "splacu_csr_create": [C.POINTER(vp), u32, u32, u32, vp, vp, vp, vp], "splacu_csr_destroy": [vp],
         "splacu_mxv_masked": [vp, i32, i32, i32, i32, vp, vp, vp, u32, i32, vp],
         "splacu_workspace_create": [C.POINTER(vp)], "splacu_workspace_destroy": [vp],

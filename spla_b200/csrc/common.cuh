@@ -79,6 +79,7 @@ namespace splacu {
         uint32_t* seg_row   = nullptr;       // [n_segs] row of every segment, ascending
         uint32_t* chain     = nullptr;       // [n_tiles] bit 31: the tile starts inside a row of the previous tile; low bits: tiles
                                              //           before t that hold the head of the row ending at t's first flag (0: none)
+        uint32_t* chain_row = nullptr;       // [n_tiles] the row that ends at t's first flag (valid where chain has a length)
         uint32_t* head      = nullptr;       // [n_tiles] sum of the tile's first segment when it continues a row (per call)
         uint32_t* tail      = nullptr;       // [n_tiles] sum after the tile's last flag (per call)
     };

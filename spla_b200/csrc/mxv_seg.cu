@@ -71,21 +71,22 @@ namespace splacu {
         }
         __global__ void __launch_bounds__(kBlock) seg_chain_kernel(const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ flags,
                                                                    const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_row, uint32_t n_tiles,
-                                                                   uint32_t* __restrict__ chain) {
+                                                                   uint32_t* __restrict__ chain, uint32_t* __restrict__ chain_row) {
             const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
             if (t >= n_tiles) return;
-            uint32_t w = 0;
+            uint32_t w = 0, row = 0;
             if (t > 0) {
                 const bool prev_ends = (flags[(t - 1u) * 16u + 15u] >> 31) & 1u;// entry 511 of tile t - 1 = (lane 31, i 15)
                 if (!prev_ends) {
                     w = 0x80000000u;
                     if (seg_base[t + 1] > seg_base[t]) {// the row that reaches into the tile ends here
-                        const uint32_t start = Ap[seg_row[seg_base[t]]];
-                        w |= t - (start >> 9);
+                        row = seg_row[seg_base[t]];
+                        w |= t - (Ap[row] >> 9);
                     }
                 }
             }
-            chain[t] = w;
+            chain[t]     = w;
+            chain_row[t] = row;
         }
     }// namespace
 
@@ -110,6 +111,7 @@ namespace splacu {
             SEG_CUDA(cudaMemsetAsync(ph.flags, 0, (size_t) nt * 16 * 4, s));
             SEG_CUDA(cudaMalloc(&ph.seg_base, ((size_t) nt + 1) * 4));
             SEG_CUDA(cudaMalloc(&ph.chain, (size_t) nt * 4));
+            SEG_CUDA(cudaMalloc(&ph.chain_row, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.head, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.tail, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&count, ((size_t) nt + 1) * 4));
@@ -124,7 +126,7 @@ namespace splacu {
             seg_flags_kernel<<<(M->n_rows + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, M->n_rows, ph.flags);
             seg_tile_count_kernel<<<(nt + 1 + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.flags, nt, count);
             SEG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, b2, count, ph.seg_base, (int) nt + 1, s));
-            seg_chain_kernel<<<(nt + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, ph.flags, ph.seg_base, ph.seg_row, nt, ph.chain);
+            seg_chain_kernel<<<(nt + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, ph.flags, ph.seg_base, ph.seg_row, nt, ph.chain, ph.chain_row);
             count_launch(5);
             SEG_CUDA(cudaMemcpyAsync(&ph.n_segs, d_num, 4, cudaMemcpyDeviceToHost, s));
             SEG_CUDA(cudaStreamSynchronize(s));
@@ -299,8 +301,8 @@ namespace splacu {
     // rows that span tiles: r[row] += tail(t0) + tail(t0 + 1) + ... + tail(t - 1) + head(t), left to right; one thread per end
     // tile, the whole warp for chains longer than 4 tiles (hub rows)
     template<typename T, typename S>
-    __global__ void __launch_bounds__(kBlock) mxv_seg_fixup_kernel(S sr, Select sel, const uint32_t* __restrict__ chain, const uint32_t* __restrict__ seg_base,
-                                                                   const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ head,
+    __global__ void __launch_bounds__(kBlock) mxv_seg_fixup_kernel(S sr, Select sel, const uint32_t* __restrict__ chain, const uint32_t* __restrict__ chain_row,
+                                                                   const uint32_t* __restrict__ head,
                                                                    const uint32_t* __restrict__ tail, const uint32_t* __restrict__ sel_bits, T* r,
                                                                    uint32_t n_tiles,
                                                                    const uint32_t* __restrict__ gate, uint32_t gate_min) {
@@ -311,7 +313,7 @@ namespace splacu {
         if (t < n_tiles) {
             len = chain[t] & 0x7fffffffu;
             if (len) {
-                row = seg_row[seg_base[t]];
+                row = chain_row[t];
                 if (sel_bits && !((sel_bits[row >> 5] >> (row & 31u)) & 1u)) len = 0;
             }
         }
@@ -354,7 +356,7 @@ namespace splacu {
         kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
                                                 ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
         SPLACU_LAUNCH_CHECK();
-        mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.seg_base, ph.seg_row, ph.head, ph.tail, sel_bits, r,
+        mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.chain_row, ph.head, ph.tail, sel_bits, r,
                                                                                         ph.n_tiles, gate, gate_min);
         SPLACU_LAUNCH_CHECK();
         return 0;

@@ -349,7 +349,53 @@ namespace splacu {
 
 using namespace splacu;
 
+namespace splacu {
+    // Multi-GPU pull: the all-gather of the result windows as ONE kernel of peer stores. Every rank writes its own window into
+    // the copy of the vector that each peer holds (symmetric allocation, same offset everywhere) with 128-bit stores over NVLink /
+    // NVSwitch; the caller closes the step with a cross-device barrier. 8 peers x 8 MB at 8 GPUs: a collective library call costs
+    // more in launch + protocol than the bytes do.
+    struct PeerPtrs {
+        uint32_t* p[SPLACU_MAX_PEERS];
+    };
+    __global__ void __launch_bounds__(kBlock) publish_window_kernel(PeerPtrs peers, int n_peers, int self, const uint32_t* __restrict__ src, size_t offset,
+                                                                    size_t count) {
+        // offset and count are multiples of 4 elements and the bases 16-byte aligned (checked on the host)
+        const size_t n4     = count / 4;
+        const size_t stride = (size_t) gridDim.x * blockDim.x;
+        const uint4* s4     = reinterpret_cast<const uint4*>(src + offset);
+        constexpr int U     = 4;// 64 bytes per thread and peer in flight
+        for (size_t i0 = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+            uint4 x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u * stride < n4) x[u] = s4[i0 + u * stride];
+            for (int q = 0; q < n_peers; ++q) {
+                if (q == self) continue;
+                uint4* d4 = reinterpret_cast<uint4*>(peers.p[q] + offset);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (i0 + u * stride < n4) d4[i0 + u * stride] = x[u];
+            }
+        }
+    }
+}// namespace splacu
+
 extern "C" {
+
+int splacu_publish_window(void* const* peer_bases, int n_peers, int self, size_t offset, size_t count, void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(peer_bases && n_peers >= 1 && n_peers <= SPLACU_MAX_PEERS, "bad peer list");
+    SPLACU_REQUIRE(self >= 0 && self < n_peers, "bad own index");
+    SPLACU_REQUIRE((offset % 4) == 0 && (count % 4) == 0, "window offset and length must be multiples of 4 elements");
+    if (count == 0 || n_peers == 1) return SPLACU_OK;
+    PeerPtrs pp;
+    for (int q = 0; q < SPLACU_MAX_PEERS; ++q) pp.p[q] = q < n_peers ? static_cast<uint32_t*>(peer_bases[q]) : nullptr;
+    for (int q = 0; q < n_peers; ++q) SPLACU_REQUIRE(pp.p[q] && (reinterpret_cast<uintptr_t>(pp.p[q]) & 15u) == 0, "peer base must be 16-byte aligned");
+    cudaStream_t s = resolve_stream(stream);
+    publish_window_kernel<<<grid_for((count / 4 + 3) / 4, kBlock, 8), kBlock, 0, s>>>(pp, n_peers, self, pp.p[self], offset, count);
+    SPLACU_LAUNCH_CHECK();
+    return SPLACU_OK;
+}
 
 int splacu_fill(void* d_dst, uint32_t value_bits, size_t n, void* stream) {
     SPLACU_CHECK_INIT();

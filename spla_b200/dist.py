@@ -113,6 +113,39 @@ def allgather_padded(full_padded, w, group=None):
     return full_padded
 
 
+class PeerVector:
+    """A full-length 4-byte-element vector that every rank of a single box holds at the same offsets in peer-mapped memory
+    (torch.distributed._symmetric_memory). publish(w0, count) writes this rank's window into every peer's copy with one kernel of
+    NVLink peer stores (splacu_publish_window) and closes the step with the device-side barrier of the symmetric allocation --
+    the all-gather of the row-sharded pull without a collective library call. NCCL / CUDA only."""
+
+    def __init__(self, backend, n, dtype=torch.float32, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+
+        self.backend, self.group = backend, group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n_pad = (n + 3) // 4 * 4
+        self.tensor = symm.empty(n_pad, dtype=dtype, device=backend.device)
+        self.handle = symm.rendezvous(self.tensor, self.group)
+        ptrs = list(self.handle.buffer_ptrs)
+        assert len(ptrs) == self.world and ptrs[self.rank] == self.tensor.data_ptr()
+        self._ptrs = (C.c_void_p * self.world)(*ptrs)
+        self._C = C
+
+    def publish(self, w0, count):
+        """window [w0, w0 + count) of the local copy -> all peers; count is rounded up to 4 elements (padded layout: the tail of a
+        window is padding). Runs on the backend's stream; returns after enqueueing."""
+        C = self._C
+        cnt = (count + 3) // 4 * 4
+        rc = self.backend.lib.splacu_publish_window(self._ptrs, self.world, self.rank, C.c_size_t(w0), C.c_size_t(cnt), self.backend.stream_ptr)
+        if rc != 0:
+            raise RuntimeError(f"splacu_publish_window failed ({rc})")
+        with torch.cuda.stream(self.backend.stream):
+            self.handle.barrier(channel=0)
+
+
 def exchange_frontier(vi_local, vx_local, offset, group=None):
     """All-gather of sparse frontier pieces. Each rank contributes (indices local to its window + offset, values);
     returns the concatenated global (vi, vx), sorted because windows are disjoint and ordered by rank.

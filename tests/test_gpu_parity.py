@@ -377,3 +377,29 @@ def test_properties_at_scale(backend):
         backend.sync()
         assert torch.equal(full, ee)
         assert torch.equal(full, (pull > 0).to(torch.int32))
+
+
+def test_publish_window_single_device(backend):
+    """splacu_publish_window (the multi-GPU all-gather as one kernel of peer stores) with three 'peers' that are plain buffers on
+    the same device: the window of the own copy lands in the other two, nothing else changes."""
+    import ctypes as C
+
+    import torch
+
+    n, w0, cnt = 4096 + 40, 128, 1000  # count is rounded up to a multiple of 4 by the caller
+    with torch.cuda.stream(backend.stream):
+        bufs = [torch.full((n,), float(q), dtype=torch.float32, device=backend.device) for q in range(3)]
+        bufs[1][:] = torch.arange(n, dtype=torch.float32, device=backend.device)
+    backend.sync()
+    ptrs = (C.c_void_p * 3)(*[b.data_ptr() for b in bufs])
+    rc = backend.lib.splacu_publish_window(ptrs, 3, 1, C.c_size_t(w0), C.c_size_t(cnt), backend.stream_ptr)
+    assert rc == 0
+    backend.sync()
+    want = torch.arange(n, dtype=torch.float32)
+    for q in (0, 2):
+        got = bufs[q].cpu()
+        assert torch.equal(got[w0:w0 + cnt], want[w0:w0 + cnt])
+        assert bool((got[:w0] == float(q)).all()) and bool((got[w0 + cnt:] == float(q)).all())
+    assert torch.equal(bufs[1].cpu(), want)
+    # misaligned windows are refused, not silently rounded
+    assert backend.lib.splacu_publish_window(ptrs, 3, 1, C.c_size_t(w0 + 1), C.c_size_t(cnt), backend.stream_ptr) != 0

@@ -4,7 +4,7 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 import json
 try:
     j=json.loads(open('gpurun_out/bench_${N}gpu.json').read().strip().splitlines()[-1])
-    print($N, 'value', j['value'], 'ms', j['ms_per_step'], 'kernel_ms', j['roofline']['kernel_ms'], 'frac', j['roofline']['frac'], 'e2e', j['e2e']['value'])
+    print($N, "value", j["value"], "ms", j["ms_per_step"], "kernel_ms", j["roofline"]["kernel_ms_per_rank"], 'frac', j['roofline']['frac'], 'e2e', j['e2e']['value'])
 except Exception as e:
     print('fail', e); print(open('gpurun_out/bench_${N}gpu.err').read()[-2000:])
 PY
