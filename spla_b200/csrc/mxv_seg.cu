@@ -201,6 +201,7 @@ namespace splacu {
             const bool     cont = (ch >> 31) != 0u;
             const uint32_t row0 = srow;
             const uint32_t fl   = (fw >> ((lane & 1u) * 16u)) & 0xffffu;
+            // (prefetch.global.L2 hints for the seg_row / r lines of the later hand-over rounds were measured: no gain)
             // r / mask of the first 32 segments: requested now, used by the hand-over at the end of the tile
             T    old0  = sr.identity();
             bool take0 = false;

@@ -1,6 +1,11 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-timeout 600 python bench.py --extra > gpurun_out/bench_r10.json 2> gpurun_out/bench_r10.err; tail -c 4500 gpurun_out/bench_r10.json; tail -5 gpurun_out/bench_r10.err
-(cd spla_b200/lib; echo "=== test_cuda_backend 12"; timeout 300 ./test_cuda_backend 12 > /tmp/o.txt 2>&1; echo "rc=$?"; tail -6 /tmp/o.txt)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r10.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-tail -2 gpurun_out/bench_under_ncu.log | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/bench_r15.json 2> gpurun_out/bench_r15.err; python - <<PY
+import json
+try:
+    j=json.loads(open('gpurun_out/bench_r15.json').read().strip().splitlines()[-1])
+    print('value', j['value'], 'ms', j['ms_per_step'], 'frac', j['roofline']['frac'], 'e2e', j['e2e']['value'], 'launches', j['gpu_launches'])
+except Exception as e:
+    print('fail', e); print(open('gpurun_out/bench_r15.err').read()[-3000:])
+PY
