@@ -933,13 +933,24 @@ namespace splacu {
         uint32_t       c      = 0;
         const uint32_t stride = gridDim.x * blockDim.x;// a multiple of 32: a warp always covers 32 consecutive rows
         const uint32_t n_pad  = (n + 31u) & ~31u;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-            const bool     p = i < n && sel.test(mask[i]);
-            const uint32_t m = __ballot_sync(0xffffffffu, p);
-            if (i < n) r[i] = init;
-            if ((threadIdx.x & 31u) == 0u) {
-                sel_bits[i >> 5] = m;
-                c += __popc(m);
+        constexpr int  U      = 4;// independent 32-row groups per warp and step
+        for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_pad; i0 += stride * U) {
+            bool p[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + u * stride;
+                p[u]             = i < n && sel.test(mask[i]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + u * stride;
+                if (i >= n_pad) break;// warp-uniform: n_pad and the strides are multiples of 32
+                const uint32_t m = __ballot_sync(0xffffffffu, p[u]);
+                if (i < n) r[i] = init;
+                if ((threadIdx.x & 31u) == 0u) {
+                    sel_bits[i >> 5] = m;
+                    c += __popc(m);
+                }
             }
         }
         if ((threadIdx.x & 31u) == 0u && c) atomicAdd(&s_count, c);

@@ -97,10 +97,21 @@ namespace splacu {
     __global__ void __launch_bounds__(kBlock) select_bits_kernel(Select sel, const T* __restrict__ mask, uint32_t n, uint32_t* __restrict__ sel_bits) {
         const uint32_t n_pad  = (n + 31) & ~31u;
         const uint32_t stride = gridDim.x * blockDim.x;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-            const bool     p = (i < n) && sel.test(mask[i]);
-            const uint32_t m = __ballot_sync(0xffffffffu, p);
-            if ((threadIdx.x & 31) == 0) sel_bits[i >> 5] = m;
+        constexpr int  U      = 4;// independent 32-element groups per warp and step
+        for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_pad; i0 += stride * U) {
+            bool p[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + u * stride;
+                p[u]             = (i < n) && sel.test(mask[i]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + u * stride;
+                if (i >= n_pad) break;// warp-uniform
+                const uint32_t m = __ballot_sync(0xffffffffu, p[u]);
+                if ((threadIdx.x & 31) == 0) sel_bits[i >> 5] = m;
+            }
         }
     }
 

@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-for d in 1.0 0.5; do
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_seg_$d.csv python tools/prof_phase.py --phases 4 --masked 1 --density $d > gpurun_out/ncu_l.log 2>&1
-done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"vxm_|bitmap|scan|select_bits|emit|fill_kernel|count" --csv --log-file gpurun_out/launches_vxm.csv python tools/prof_vxm.py 2>&1 | grep -v "^==" | tail -4
