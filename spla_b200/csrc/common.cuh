@@ -82,9 +82,6 @@ namespace splacu {
         uint32_t* chain_row = nullptr;       // [n_tiles] the row that ends at t's first flag (valid where chain has a length)
         uint32_t* head      = nullptr;       // [n_tiles] sum of the tile's first segment when it continues a row (per call)
         uint32_t* tail      = nullptr;       // [n_tiles] sum after the tile's last flag (per call)
-        unsigned long long* tail64 = nullptr;// [n_tiles] (epoch << 32 | tail bits): published by the tile's warp, awaited by the warp of
-                                             //           the tile where the row ends (in-kernel look-back instead of a fix-up launch)
-        mutable uint32_t epoch = 0;          // call counter: tags the tail64 entries of the current call
     };
     static constexpr int kMaxHubPhases = 16;
 
@@ -130,7 +127,7 @@ namespace splacu {
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_SEG_LOOKBACK, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------

@@ -114,8 +114,6 @@ namespace splacu {
             SEG_CUDA(cudaMalloc(&ph.chain_row, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.head, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.tail, (size_t) nt * 4));
-            SEG_CUDA(cudaMalloc(&ph.tail64, (size_t) nt * 8));
-            SEG_CUDA(cudaMemsetAsync(ph.tail64, 0, (size_t) nt * 8, s));// epoch 0 = never written; calls count from 1
             SEG_CUDA(cudaMalloc(&count, ((size_t) nt + 1) * 4));
             SEG_CUDA(cudaMalloc(&d_num, 4));
             // every non-empty row is one segment; + 32: the kernel reads the rows of a tile 32 at a time
@@ -152,18 +150,9 @@ namespace splacu {
                            const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ chain,
                            uint32_t* __restrict__ head, uint32_t* __restrict__ tail, const T* __restrict__ v, const uint32_t* __restrict__ sel_bits, T* r,
                            uint32_t n_tiles, const uint32_t* __restrict__ hub_vals, uint32_t n_slots, const uint32_t* __restrict__ gate,
-                           uint32_t gate_min, unsigned long long* __restrict__ tail64, uint32_t epoch) {
+                           uint32_t gate_min) {
         extern __shared__ __align__(16) uint32_t smem[];
-        if (MASKED && gate && *gate < gate_min) return;
-        // look-back (tail64 != null): the warp of the tile where a row ENDS waits for the tails of the earlier tiles of that row, which
-        // their warps publish as (epoch, value) in one 64-bit word. Tiles are handed out in increasing order to a fully resident
-        // persistent grid and a tail is published before its own warp waits for anything, so the smallest unfinished tile never waits.
-        auto wait_tail = [&](uint32_t u) -> T {
-            const volatile unsigned long long* p = tail64 + u;
-            unsigned long long                 x;
-            do { x = *p; } while ((uint32_t) (x >> 32) != epoch);
-            return from_bits<T>((uint32_t) x);
-        };// sparse mask: the CSR kernel (mask tested before any gather) runs instead
+        if (MASKED && gate && *gate < gate_min) return;// sparse mask: the CSR kernel (mask tested before any gather) runs instead
         constexpr int  NI   = IDX16 ? 2 : 4;// 128-bit index loads per lane and tile
         const uint32_t tid  = threadIdx.x;
         const uint32_t lane = tid & 31u;
@@ -207,38 +196,9 @@ namespace splacu {
         load_meta(first);
         prefetch(first);
 
-        uint32_t pend_clen = 0, pend_tile = 0, pend_row = 0;// warp-uniform: chain length / end tile; lane 0: the row ...
-        bool     pend_take = false;                         // ... whether the mask selects it ...
-        T        pend_sum = sr.identity(), pend_old = sr.identity();// ... its r value and the part of its sum that lies in the end tile
-        unsigned long long pre = 0;// lanes 0 .. 3: first look at the (at most 4) tails of a short chain, requested at the top of the tile
-        auto     resolve_pending = [&]() {
-            if (pend_clen == 0u) return;
-            T chain_sum = sr.identity();// tails of the earlier tiles of the row, left to right
-            if (pend_clen <= 4u) {
-                if (lane < pend_clen) {
-                    const volatile unsigned long long* p = tail64 + (pend_tile - pend_clen + lane);
-                    while ((uint32_t) (pre >> 32) != epoch) pre = *p;
-                }
-                const T tv = from_bits<T>((uint32_t) pre);
-                chain_sum  = __shfl_sync(0xffffffffu, tv, 0);
-                for (uint32_t k = 1; k < pend_clen; ++k) chain_sum = sr.add(chain_sum, __shfl_sync(0xffffffffu, tv, (int) k));
-            } else {// a hub row: the whole warp, fixed order
-                for (uint32_t u = lane; u < pend_clen; u += 32) chain_sum = sr.add(chain_sum, wait_tail(pend_tile - pend_clen + u));
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) chain_sum = sr.add(chain_sum, __shfl_xor_sync(0xffffffffu, chain_sum, o));
-            }
-            if (lane == 0 && pend_take) r[pend_row] = sr.add(pend_old, sr.add(chain_sum, pend_sum));
-            pend_clen = 0u;
-            pre       = 0;
-        };
-
         for (uint32_t tile = first; tile < n_tiles; tile += n_warps) {
             const uint32_t base = sb0, nfl = sb1 - sb0;
             const bool     cont = (ch >> 31) != 0u;
-            const uint32_t clen = ch & 0x7fffffffu;// tiles before this one that hold the head of the row ending at the first flag
-            // first look at the tails the pending row of the previous tile waits for (consumed after this tile's scan)
-            if (tail64 && pend_clen != 0u && pend_clen <= 4u && lane < pend_clen)
-                pre = *reinterpret_cast<const volatile unsigned long long*>(tail64 + (pend_tile - pend_clen + lane));
             const uint32_t row0 = srow;
             const uint32_t fl   = (fw >> ((lane & 1u) * 16u)) & 0xffffu;
             // (prefetch.global.L2 hints for the seg_row / r lines of the later hand-over rounds were measured: no gain)
@@ -317,16 +277,9 @@ namespace splacu {
                     acc = sr.identity();
                 }
             }
-            // what follows the tile's last flag (the whole tile when it has none)
-            if (lane == 31) {
-                if (tail64) *reinterpret_cast<volatile unsigned long long*>(tail64 + tile) = ((unsigned long long) epoch << 32) | to_bits(acc);
-                else tail[tile] = to_bits(acc);
-            }
+            if (lane == 31) tail[tile] = to_bits(acc);// what follows the tile's last flag (the whole tile when it has none)
             __syncwarp();
-            // close the row that ended at the first flag of this warp's PREVIOUS tile: by now (a whole tile later) the warps of the
-            // earlier tiles of that row have long published their tails, so the wait is free and the warps stay decoupled
-            // (resolving at once chained every tile to its left neighbour: a convoy, 1.5 -> 2.7 ms)
-            resolve_pending();
+
             // ---- hand-over: the lane that owns segment o adds its sum onto r. (A two-stage software pipeline over the rounds of
             //      32 segments was slower: more registers, spills.) ----
             for (uint32_t o = lane; o < nfl; o += 32) {
@@ -339,17 +292,11 @@ namespace splacu {
                     old  = r[row];
                 }
                 const T sum = s_out[o];
-                if (o == 0 && cont) {// the row began in an earlier tile
-                    if (!tail64) head[tile] = to_bits(sum);// ... the fix-up launch adds the chain
-                    else pend_sum = sum, pend_row = row, pend_take = take, pend_old = old;// ... or this warp does, one tile later
-                } else if (take) {
-                    r[row] = sr.add(old, sum);
-                }
+                if (o == 0 && cont) head[tile] = to_bits(sum);// the row began in an earlier tile: the fix-up adds the chain
+                else if (take) r[row] = sr.add(old, sum);
             }
-            if (tail64 && clen > 0u) pend_clen = clen, pend_tile = tile;
             __syncwarp();// s_out is reused by the next tile
         }
-        resolve_pending();
     }
 
     // rows that span tiles: r[row] += tail(t0) + tail(t0 + 1) + ... + tail(t - 1) + head(t), left to right; one thread per end
@@ -407,13 +354,9 @@ namespace splacu {
         }
         const uint32_t want = (ph.n_tiles + kW - 1) / kW;
         const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
-        const bool lookback = get_option(OPT_MXV_SEG_LOOKBACK) != 0 && ph.tail64;
-        if (lookback) ++ph.epoch;
         kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
-                                                ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min,
-                                                lookback ? ph.tail64 : nullptr, ph.epoch);
+                                                ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
         SPLACU_LAUNCH_CHECK();
-        if (lookback) return 0;
         mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.chain_row, ph.head, ph.tail, sel_bits, r,
                                                                                         ph.n_tiles, gate, gate_min);
         SPLACU_LAUNCH_CHECK();
