@@ -27,7 +27,7 @@ namespace splacu {
 
     namespace {
         constexpr int      kBlock    = 256;
-        constexpr int      kSegWarps = 24;// warps per persistent CTA of a hub class (shared-memory gathers)
+        constexpr int      kSegWarps = 20;// warps per persistent CTA of a hub class (shared-memory gathers)
 #ifndef SPLACU_SEG_TAIL_WARPS
 #define SPLACU_SEG_TAIL_WARPS 20
 #endif
@@ -280,20 +280,30 @@ namespace splacu {
             if (lane == 31) tail[tile] = to_bits(acc);// what follows the tile's last flag (the whole tile when it has none)
             __syncwarp();
 
-            // ---- hand-over: the lane that owns segment o adds its sum onto r. (A two-stage software pipeline over the rounds of
-            //      32 segments was slower: more registers, spills.) ----
-            for (uint32_t o = lane; o < nfl; o += 32) {
-                uint32_t row  = row0;
-                bool     take = take0;
-                T        old  = old0;
-                if (o >= 32) {
-                    row  = __ldg(seg_row + base + o);
-                    take = MASKED ? ((sel_bits[row >> 5] >> (row & 31u)) & 1u) != 0u : true;
-                    old  = r[row];
+            // ---- hand-over: the lane that owns segment o adds its sum onto r. Two-stage pipeline over the rounds of 32 segments:
+            //      the rows of round i + 2 and the r / selection values of round i + 1 are requested before round i is written
+            //      (needs the registers of 20-warp CTAs; at 24 warps / 80 registers it spilled and lost) ----
+            {
+                uint32_t rowA = row0, rowB = (nfl > 32u + lane) ? __ldg(seg_row + base + 32u + lane) : 0u;
+                bool     takeA = take0;
+                T        oldA  = old0;
+                for (uint32_t ob = 0; ob < nfl; ob += 32) {
+                    const uint32_t o = ob + lane;
+                    uint32_t       rowC = 0;
+                    bool           takeB = false;
+                    T              oldB  = sr.identity();
+                    if (o + 64 < nfl) rowC = __ldg(seg_row + base + o + 64);
+                    if (o + 32 < nfl) {
+                        takeB = MASKED ? ((sel_bits[rowB >> 5] >> (rowB & 31u)) & 1u) != 0u : true;
+                        oldB  = r[rowB];
+                    }
+                    if (o < nfl) {
+                        const T sum = s_out[o];
+                        if (o == 0 && cont) head[tile] = to_bits(sum);// the row began in an earlier tile: the fix-up adds the chain
+                        else if (takeA) r[rowA] = sr.add(oldA, sum);
+                    }
+                    rowA = rowB, takeA = takeB, oldA = oldB, rowB = rowC;
                 }
-                const T sum = s_out[o];
-                if (o == 0 && cont) head[tile] = to_bits(sum);// the row began in an earlier tile: the fix-up adds the chain
-                else if (take) r[row] = sr.add(old, sum);
             }
             __syncwarp();// s_out is reused by the next tile
         }
