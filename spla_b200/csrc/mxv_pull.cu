@@ -1029,7 +1029,7 @@ namespace splacu {
         }
         if (M->n_phases && M->phase[0].seg) {
             // dense masks (and ALWAYS): the column-class passes. Sparse masks: the CSR kernel below tests the mask before it
-            // touches Aj / Ax / v and wins as soon as a quarter of the rows is unselected. The device decides.
+            // touches Aj / Ax / v and wins once more than half of the rows are unselected. The device decides.
             const uint32_t* gate     = nullptr;
             uint32_t        gate_min = 0;
             if (sel.reads_mask && M->sel_count) {

@@ -403,3 +403,61 @@ def test_publish_window_single_device(backend):
     assert torch.equal(bufs[1].cpu(), want)
     # misaligned windows are refused, not silently rounded
     assert backend.lib.splacu_publish_window(ptrs, 3, 1, C.c_size_t(w0 + 1), C.c_size_t(cnt), backend.stream_ptr) != 0
+
+
+@pytest.mark.parametrize("density", [0.0, 0.3, 0.44, 0.46, 0.9, 1.0])
+def test_pull_mask_density_gate(backend, oracle, density):
+    """With column classes the device chooses per call between the class passes (dense masks) and the mask-first CSR kernel
+    (sparse masks) from the number of selected rows; both sides of the threshold, and the extremes, must match the oracle."""
+    rng = np.random.default_rng(int(density * 1000) + 5)
+    n_rows, n_cols = 4000, 3000
+    Ap, Aj, Ax = _skewed_csr(rng, INT, n_rows, n_cols, "small")
+    try:
+        backend.set_option("mxv_hub", 3)
+        backend.set_option("mxv_phase_slots", 128)
+        backend.set_option("mxv_phases", 3)
+        backend.set_option("mxv_hub_min_count", 2)
+        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+        assert len(backend.csr_info(M)["phase_nnz"]) >= 2
+    finally:
+        backend.set_option("mxv_hub", 1)
+        backend.set_option("mxv_phase_slots", 45056)
+        backend.set_option("mxv_phases", 4)
+        backend.set_option("mxv_hub_min_count", 16)
+    v = cases.rand_values(rng, INT, n_cols, "small")
+    mask = (rng.random(n_rows) < density).astype(np.int32)
+    for osel, m in (("NQZERO", mask), ("EQZERO", 1 - mask)):
+        want = oracle.mxv_masked(INT, "MULT", "PLUS", osel, Ap, Aj, Ax, v, m, 7, False)
+        got = backend.mxv_masked(M, to_dev(v, backend), to_dev(m, backend), "MULT", "PLUS", osel, 7)
+        backend.sync()
+        assert np.array_equal(to_np(got, np.int32), want), f"density {density} {osel}"
+
+
+@pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "MULT", "PLUS", "EQZERO"), (FLOAT, "MULT", "PLUS", "NQZERO"), (UINT, "BAND", "BOR", "ALWAYS")])
+def test_pull_column_classes_csr_format(backend, oracle, dtype, om, oa, osel):
+    """The column classes can also be kept as plain CSR slices run by the CSR tile kernel (option mxv_seg = 0: the format the
+    segmented tiles replaced, kept as the comparison point of DESIGN.md); it must stay exact too."""
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, om, oa, "csr-classes")).encode()))
+    n_rows, n_cols = 3000, 2500
+    kind = "unit" if dtype == FLOAT else "small"
+    Ap, Aj, Ax = _skewed_csr(rng, dtype, n_rows, n_cols, kind)
+    try:
+        backend.set_option("mxv_hub", 3)
+        backend.set_option("mxv_seg", 0)
+        backend.set_option("mxv_phase_slots", 64)
+        backend.set_option("mxv_phases", 3)
+        backend.set_option("mxv_hub_min_count", 2)
+        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+        assert len(backend.csr_info(M)["phase_nnz"]) >= 2
+    finally:
+        backend.set_option("mxv_hub", 1)
+        backend.set_option("mxv_seg", 1)
+        backend.set_option("mxv_phase_slots", 45056)
+        backend.set_option("mxv_phases", 4)
+        backend.set_option("mxv_hub_min_count", 16)
+    v = cases.rand_values(rng, dtype, n_cols, kind)
+    mask = cases.rand_values(rng, dtype, n_rows)
+    want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, 2, False)
+    got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, 2)
+    backend.sync()
+    assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what="csr-format classes")
