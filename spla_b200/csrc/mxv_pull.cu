@@ -184,13 +184,16 @@ namespace splacu {
         void*     Aj[kMaxHubPhases + 1];
         uint32_t* Ax[kMaxHubPhases + 1];
     };
-    __device__ __forceinline__ uint32_t phase_of(uint32_t slot, uint32_t slots_per_phase, uint32_t n_hub_phases) {
-        return slot == 0xffffffffu ? n_hub_phases : slot / slots_per_phase;
+    // Tail entries are further split by column RANGE (2^range_shift columns each) once v is larger than what the L2 keeps:
+    // a pass then gathers from one L2-resident window of v instead of all of it (measured on RMAT-25 / 26, where v is 128 /
+    // 256 MB: gathers that miss the L2 run at 67-96 G/s instead of ~280 G/s).
+    __device__ __forceinline__ uint32_t phase_of(uint32_t slot, uint32_t col, uint32_t slots_per_phase, uint32_t n_hub_phases, uint32_t range_shift) {
+        return slot == 0xffffffffu ? n_hub_phases + (col >> range_shift) : slot / slots_per_phase;
     }
     // a warp per row: cnt[p][row] = entries of the row in class p
     __global__ void __launch_bounds__(kBlock) phase_count_kernel(const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj, uint32_t n_rows,
                                                                  const uint32_t* __restrict__ slot, uint32_t slots_per_phase, uint32_t n_hub_phases,
-                                                                 uint32_t* __restrict__ cnt) {
+                                                                 uint32_t n_classes, uint32_t range_shift, uint32_t* __restrict__ cnt) {
         const uint32_t lane    = threadIdx.x & 31u;
         const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
         for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
@@ -198,25 +201,30 @@ namespace splacu {
             uint32_t       mine = 0;
             for (uint32_t kb = k0; kb < k1; kb += 32) {
                 const uint32_t k = kb + lane;
-                const uint32_t p = k < k1 ? phase_of(slot[Aj[k]], slots_per_phase, n_hub_phases) : 0xffu;
-                for (uint32_t q = 0; q <= n_hub_phases; ++q) {
+                uint32_t       p = 0xffu;
+                if (k < k1) {
+                    const uint32_t col = Aj[k];
+                    p                  = phase_of(slot[col], col, slots_per_phase, n_hub_phases, range_shift);
+                }
+                for (uint32_t q = 0; q < n_classes; ++q) {
                     const uint32_t m = __ballot_sync(0xffffffffu, p == q);
                     if (lane == q) mine += __popc(m);
                 }
             }
-            if (lane <= n_hub_phases) cnt[(size_t) lane * (n_rows + 1) + row] = mine;
+            if (lane < n_classes) cnt[(size_t) lane * (n_rows + 1) + row] = mine;
         }
     }
     // a warp per row: stable partition of the row's entries into the class arrays (column order is kept inside a class)
     __global__ void __launch_bounds__(kBlock) phase_scatter_kernel(const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj,
                                                                    const uint32_t* __restrict__ Ax, uint32_t n_rows, const uint32_t* __restrict__ slot,
-                                                                   uint32_t slots_per_phase, uint32_t n_hub_phases, PhasePtrs out, int seg) {
+                                                                   uint32_t slots_per_phase, uint32_t n_hub_phases, uint32_t n_classes,
+                                                                   uint32_t range_shift, PhasePtrs out, int seg) {
         const uint32_t lane    = threadIdx.x & 31u;
         const uint32_t lt      = (1u << lane) - 1u;
         const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
         for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
             const uint32_t k0 = Ap[row], k1 = Ap[row + 1];
-            uint32_t       off = lane <= n_hub_phases ? out.Ap[lane][row] : 0u;// lane q tracks the write position of class q
+            uint32_t       off = lane < n_classes ? out.Ap[lane][row] : 0u;// lane q tracks the write position of class q
             for (uint32_t kb = k0; kb < k1; kb += 32) {
                 const uint32_t k  = kb + lane;
                 const bool     ok = k < k1;
@@ -226,8 +234,8 @@ namespace splacu {
                     sl  = slot[col];
                     val = Ax[k];
                 }
-                const uint32_t p = ok ? phase_of(sl, slots_per_phase, n_hub_phases) : 0xffu;
-                for (uint32_t q = 0; q <= n_hub_phases; ++q) {
+                const uint32_t p = ok ? phase_of(sl, col, slots_per_phase, n_hub_phases, range_shift) : 0xffu;
+                for (uint32_t q = 0; q < n_classes; ++q) {
                     const uint32_t m    = __ballot_sync(0xffffffffu, p == q);
                     const uint32_t base = __shfl_sync(0xffffffffu, off, q);
                     if (p == q) {
@@ -255,7 +263,11 @@ namespace splacu {
     // slot[col] = rank of the column among the n_hub most referenced ones (else 0xffffffff), hub_cols = those columns
     static int build_phases(Csr* M, const uint32_t* d_slot, uint32_t n_hub, uint32_t slots_per_phase, cudaStream_t s) {
         const uint32_t n_hub_phases = (n_hub + slots_per_phase - 1) / slots_per_phase;
-        const uint32_t n_classes    = n_hub_phases + 1;
+        // tail classes: one per window of 2^range_shift columns; widen the windows until the classes fit the handle
+        uint32_t range_shift = (uint32_t) get_option(OPT_MXV_TAIL_RANGE_LOG2);
+        if (range_shift < 10 || range_shift > 31) range_shift = 31;
+        while (range_shift < 31 && n_hub_phases + (((uint64_t) M->n_cols - 1) >> range_shift) + 1 > (uint64_t) kMaxHubPhases + 1) ++range_shift;
+        const uint32_t n_classes = n_hub_phases + ((M->n_cols - 1) >> range_shift) + 1;
         const size_t   stride       = (size_t) M->n_rows + 1;
         uint32_t*      cnt          = nullptr;
         void*          tmp          = nullptr;
@@ -277,7 +289,7 @@ namespace splacu {
             M->n_phases = (int) n_classes;
             PH_CUDA(cudaMalloc(&cnt, n_classes * stride * 4));
             PH_CUDA(cudaMemsetAsync(cnt, 0, n_classes * stride * 4, s));
-            phase_count_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->n_rows, d_slot, slots_per_phase, n_hub_phases, cnt);
+            phase_count_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->n_rows, d_slot, slots_per_phase, n_hub_phases, n_classes, range_shift, cnt);
             PH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, cnt, (int) stride, s));
             PH_CUDA(cudaMalloc(&tmp, tmp_bytes));
             for (uint32_t p = 0; p < n_classes; ++p) {
@@ -304,7 +316,7 @@ namespace splacu {
                 }
                 ptrs.Ap[p] = ph.Ap, ptrs.Aj[p] = ph.Aj, ptrs.Ax[p] = ph.Ax;
             }
-            phase_scatter_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->Ax, M->n_rows, d_slot, slots_per_phase, n_hub_phases, ptrs, seg);
+            phase_scatter_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->Ax, M->n_rows, d_slot, slots_per_phase, n_hub_phases, n_classes, range_shift, ptrs, seg);
             count_launch(1);
             for (uint32_t p = 0; p < n_classes; ++p) {
                 CsrPhase& ph = M->phase[p];

@@ -31,8 +31,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }

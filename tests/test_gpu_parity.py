@@ -461,3 +461,64 @@ def test_pull_column_classes_csr_format(backend, oracle, dtype, om, oa, osel):
     got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, 2)
     backend.sync()
     assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what="csr-format classes")
+
+
+@pytest.mark.parametrize("seg", [1, 0])
+@pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "MULT", "PLUS", "EQZERO"), (FLOAT, "MULT", "PLUS", "ALWAYS"), (FLOAT, "PLUS", "MIN", "NQZERO"),
+                                              (UINT, "BAND", "BOR", "ALWAYS")])
+def test_pull_tail_column_ranges(backend, oracle, dtype, om, oa, osel, seg):
+    """Vectors larger than the L2 split the tail class into windows of 2^k columns, one pass each (option mxv_tail_range_log2,
+    24 by default); forced down to 1024-column windows here so that a 2500-column matrix gets 2 hub classes + 3 tail windows.
+    Every class accumulates onto r in a fixed order: exact for INT / UINT / MIN, 1e-5 for FLOAT sums."""
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, om, oa, "tail-ranges", seg)).encode()))
+    n_rows, n_cols = 3000, 2500
+    kind = "positive" if (om, oa) == ("PLUS", "MIN") else ("unit" if dtype == FLOAT else "small")
+    Ap, Aj, Ax = _skewed_csr(rng, dtype, n_rows, n_cols, kind)
+    try:
+        backend.set_option("mxv_hub", 3)
+        backend.set_option("mxv_seg", seg)
+        backend.set_option("mxv_phase_slots", 64)
+        backend.set_option("mxv_phases", 2)
+        backend.set_option("mxv_hub_min_count", 2)
+        backend.set_option("mxv_tail_range_log2", 10)
+        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+        info = backend.csr_info(M)
+        assert len(info["phase_nnz"]) == 2 + 3 and sum(info["phase_nnz"]) == len(Aj), info
+        assert all(x > 0 for x in info["phase_nnz"][2:]), info
+    finally:
+        backend.set_option("mxv_hub", 1)
+        backend.set_option("mxv_seg", 1)
+        backend.set_option("mxv_phase_slots", 45056)
+        backend.set_option("mxv_phases", 4)
+        backend.set_option("mxv_hub_min_count", 16)
+        backend.set_option("mxv_tail_range_log2", 24)
+    for rep in range(2):
+        v = cases.rand_values(rng, dtype, n_cols, kind)
+        mask = cases.rand_values(rng, dtype, n_rows)
+        init = np.float32(3.0e38) if (om, oa) == ("PLUS", "MIN") else (0 if rep == 0 else 5)
+        want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
+        got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
+        backend.sync()
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"tail ranges rep {rep}")
+
+
+def test_pull_tail_ranges_widen_to_fit(backend):
+    """More windows than the handle has classes for: the windows are widened (doubling) until they fit."""
+    rng = np.random.default_rng(5)
+    n_rows, n_cols = 2000, 60000
+    Ap, Aj, Ax = cases.rand_csr(rng, INT, n_rows, n_cols, 20, skew=True, kind="small")
+    try:
+        backend.set_option("mxv_hub", 3)
+        backend.set_option("mxv_phase_slots", 64)
+        backend.set_option("mxv_phases", 2)
+        backend.set_option("mxv_hub_min_count", 1)
+        backend.set_option("mxv_tail_range_log2", 10)  # 59 windows asked for, 17 classes available
+        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+        info = backend.csr_info(M)
+        assert 2 < len(info["phase_nnz"]) <= 17 and sum(info["phase_nnz"]) == len(Aj), info
+    finally:
+        backend.set_option("mxv_hub", 1)
+        backend.set_option("mxv_phase_slots", 45056)
+        backend.set_option("mxv_phases", 4)
+        backend.set_option("mxv_hub_min_count", 16)
+        backend.set_option("mxv_tail_range_log2", 24)
