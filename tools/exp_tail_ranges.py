@@ -14,6 +14,7 @@ from spla_b200.backend import Backend  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--graphs", default="rmat:25,uniform:25,rmat:24,rmat:26")
 ap.add_argument("--shifts", default="31,24,23,22")
+ap.add_argument("--masked", action="store_true", help="NQZERO with an all-ones mask (the bench workload) instead of ALWAYS")
 args = ap.parse_args()
 be = Backend(0)
 dev = be.device
@@ -35,20 +36,20 @@ for spec in args.graphs.split(","):
         v = torch.rand(n, generator=g, device=dev)
         r = torch.empty_like(v)
         first = None
+        mask = torch.ones(n, dtype=torch.float32, device=dev) if args.masked else None
+        sel = "NQZERO" if args.masked else "ALWAYS"
         for shift in [int(x) for x in args.shifts.split(",")]:
-            if shift != 31 and (n - 1) >> shift == 0 and first is not None:
-                continue  # a single window: same as 31
             be.set_option("mxv_tail_range_log2", shift)
             M = be.csr(n, n, Ap32, Aj, Ax)
             info = be.csr_info(M)
             for _ in range(2):
-                be.mxv_masked(M, v, None, "MULT", "PLUS", "ALWAYS", 0.0, out=r)
+                be.mxv_masked(M, v, mask, "MULT", "PLUS", sel, 0.0, out=r)
             be.sync()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 10 if scale <= 24 else 5
+            reps = 20 if scale <= 24 else 5
             e0.record(be.stream)
             for _ in range(reps):
-                be.mxv_masked(M, v, None, "MULT", "PLUS", "ALWAYS", 0.0, out=r)
+                be.mxv_masked(M, v, mask, "MULT", "PLUS", sel, 0.0, out=r)
             e1.record(be.stream)
             be.sync()
             ms = e0.elapsed_time(e1) / reps

@@ -73,6 +73,43 @@ static float run(const uint32_t* idx, const float* table, size_t n, float* out, 
     return best;
 }
 
+// second table: plain gathers only -- how much do the thread count and the L1 share left by the shared-memory carve-out matter?
+template<int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) gather_plain(const uint4* __restrict__ idx, const float* __restrict__ table, size_t n4, float* out) {
+    float acc = 0.f;
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x * 4) {
+        uint4 j[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            size_t q = i + (size_t) c * gridDim.x * blockDim.x;
+            j[c]     = q < n4 ? __ldcs(idx + q) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc += __ldg(table + j[c].x) + __ldg(table + j[c].y) + __ldg(table + j[c].z) + __ldg(table + j[c].w);
+    }
+    if (acc == 123.456f) *out = acc;
+}
+template<int THREADS>
+static void sweep_plain(const uint32_t* idx, const float* table, size_t n, float* out, int grid) {
+    cudaFuncSetAttribute(gather_plain<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int smem_kib : {0, 16, 32, 40, 64, 100, 132}) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0);
+            gather_plain<THREADS><<<grid, THREADS, (size_t) smem_kib * 1024>>>((const uint4*) idx, table, n / 4, out);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep && ms < best) best = ms;
+        }
+        printf("plain gathers, %4d threads / SM, %3d KiB dynamic shared memory: %.3f ms  %.0f G/s\n", THREADS, smem_kib, best, n / best / 1e6);
+    }
+}
+
 int main() {
     const size_t n = (size_t) 1 << 28;// 256 Mi gathers
     uint32_t*    idx;
@@ -101,6 +138,11 @@ int main() {
                    p1024 / 1024.0, eff_n / 256, ms0, n / ms0 / 1e6, ms1, n / ms1 / 1e6, ms2, n / ms2 / 1e6, ms3, n / ms3 / 1e6);
         }
     }
+    fill_idx<<<grid * 8, 256>>>(idx, n, cold_mask, 0u, 0u);
+    sweep_plain<512>(idx, table, n, out, grid);
+    sweep_plain<640>(idx, table, n, out, grid);
+    sweep_plain<768>(idx, table, n, out, grid);
+    sweep_plain<1024>(idx, table, n, out, grid);
     cudaError_t e = cudaDeviceSynchronize();
     printf("%s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
