@@ -101,3 +101,82 @@ def pagerank(be, M, alpha=0.85, eps=1e-6, max_iter=1000):
             it += 1
         be.sync()
     return p_prev, it
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Multi-GPU BFS (BASELINE config 4): one process per GPU, vertices owned in contiguous nnz-balanced windows.
+def make_bfs_shard(be, n, Ap, Aj, Ax, rank, world):
+    """Rank `rank`'s share of a SYMMETRIC n x n matrix: window [b[rank], b[rank+1]) of the vertices (nnz-balanced on Ap, and --
+    the matrix being symmetric -- on the columns too), M_rows = M[window, :] for the pull direction (row-sharded mxv)
+    and M_cols = M[:, window] for the push direction (column-sharded vxm)."""
+    from . import dist as sd
+
+    b = sd.balanced_boundaries(Ap, world)
+    w0, w1 = b[rank], b[rank + 1]
+    rAp, rAj, rAx = sd.row_slice(Ap, Aj, Ax, w0, w1)
+    cAp, cAj, cAx = sd.column_slice(Ap, Aj, Ax, w0, w1)
+    return {"n": n, "bounds": b, "rank": rank, "world": world, "w0": w0, "w1": w1,
+            "M_rows": be.csr(w1 - w0, n, rAp, rAj.to(torch.int32), rAx),
+            "M_cols": be.csr(n, w1 - w0, cAp, cAj, cAx)}
+
+
+def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None, trace=None):
+    """BFS over a sharded matrix; returns this rank's window of the depth vector (int32, 0 = unreached, source = 1).
+
+    Per level, exactly the reference's sequence (src/algorithm.cpp:45-120) on the owner's window -- v_assign_masked, then
+    vxm_masked (push) or mxv_masked with early exit (pull), then the front size -- with one exchange step in between:
+      push  all-gather of the sparse frontier pieces (dist.exchange_frontier); every rank expands the whole frontier against its
+            column slice under its own window of the depth vector as the mask; results are disjoint windows
+      pull  all-gather of the dense frontier windows (dist.allgather_windows); every rank pulls its rows
+    and a 1-element all-reduce for the global front size, which every rank uses for the same push / pull decision."""
+    import contextlib
+
+    import torch.distributed as tdist
+
+    from . import dist as sd
+
+    n, b, rank = shard["n"], shard["bounds"], shard["rank"]
+    w0, w1 = shard["w0"], shard["w1"]
+    n_loc = w1 - w0
+    dev = be.device
+    ctx = torch.cuda.stream(be.stream) if getattr(be, "stream", None) is not None else contextlib.nullcontext()
+    with ctx:
+        depth = torch.zeros(n_loc, dtype=torch.int32, device=dev)
+        full = torch.zeros(n, dtype=torch.int32, device=dev)
+        own = w0 <= source < w1
+        li = torch.tensor([source - w0] if own else [], dtype=torch.int32, device=dev)
+        front = Frontier(be, n_loc, 0, coo=(li, torch.ones(li.numel(), dtype=torch.int32, device=dev)))
+        size, level = 1, 1
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        while size:
+            if front.coo is not None:
+                if front.coo[0].numel():
+                    be.v_assign_masked(depth, front.coo, level, "SECOND", "NQZERO")
+            else:
+                be.v_assign_masked(depth, front.dense, level, "SECOND", "NQZERO")
+            push = mode == "push" or (mode == "push_pull" and size / n <= front_factor)
+            if push:
+                vi, vx = sd.exchange_frontier(*front.as_coo(), w0, group=group)
+                if n_loc and vi.numel():
+                    ri, rx = be.vxm_masked(shard["M_cols"], vi, vx, depth, "BAND", "BOR", "EQZERO")
+                else:
+                    ri, rx = vi[:0], vx[:0]
+                front = Frontier(be, n_loc, 0, coo=(ri, rx))
+            else:
+                if n_loc:
+                    full[w0:w1].copy_(front.as_dense())
+                sd.allgather_windows(full, b, group=group)
+                if n_loc:
+                    r = be.mxv_masked(shard["M_rows"], full, depth, "BAND", "BOR", "EQZERO", 0, early_exit=True)
+                else:
+                    r = depth[:0]
+                front = Frontier(be, n_loc, 0, dense=r)
+            cnt[0] = front.count() if n_loc else 0
+            if shard["world"] > 1:
+                tdist.all_reduce(cnt, group=group)
+            size = int(cnt.item())
+            if trace is not None:
+                trace.append(("push" if push else "pull", size))
+            level += 1
+        be.sync()
+    return depth

@@ -104,3 +104,110 @@ def test_balanced_boundaries_edge_cases():
         assert len(b) == parts + 1 and b[0] == 0 and b[-1] == 6 and all(b[i] <= b[i + 1] for i in range(parts))
     b = sd.balanced_boundaries(torch.zeros(5, dtype=torch.int64), 4)  # empty matrix
     assert b[0] == 0 and b[-1] == 4
+
+
+# ---- multi-GPU BFS host logic (spla_b200.algorithms.bfs_dist) with the C oracle doing every rank's arithmetic ----
+class _OracleBackend:
+    """Stand-in for spla_b200.backend.Backend on CPU tensors: same method names and argument meaning, every op computed by the
+    oracle. What the test exercises is bfs_dist's ownership / exchange / push-pull logic, not the kernels."""
+
+    def __init__(self):
+        from oracle.oracle import INT, Oracle
+
+        self.orc, self.INT = Oracle(), INT
+        self.device, self.stream = "cpu", None
+
+    class _M:
+        pass
+
+    def csr(self, n_rows, n_cols, Ap, Aj, Ax):
+        m = self._M()
+        m.n_rows, m.n_cols = n_rows, n_cols
+        m.Ap, m.Aj, m.Ax = (t.numpy().astype(np.uint32) for t in (Ap, Aj, Ax))
+        return m
+
+    def sync(self):
+        pass
+
+    def v_assign_masked(self, r, mask, value, op_assign, op_select):
+        if isinstance(mask, tuple):
+            out = self.orc.v_assign_masked_sparse(self.INT, op_assign, op_select, r.numpy(), mask[0].numpy(), mask[1].numpy(), value)
+        else:
+            out = self.orc.v_assign_masked_dense(self.INT, op_assign, op_select, r.numpy(), mask.numpy(), value)
+        r.copy_(torch.from_numpy(out.astype(np.int32)))
+        return r
+
+    def vxm_masked(self, M, vi, vx, mask, op_mult, op_add, op_select):
+        ri, rx = self.orc.vxm_masked(self.INT, op_mult, op_add, op_select, M.Ap, M.Aj, M.Ax, M.n_cols, vi.numpy().astype(np.uint32), vx.numpy(),
+                                     mask.numpy())
+        return torch.from_numpy(ri.astype(np.int32)), torch.from_numpy(rx.astype(np.int32))
+
+    def mxv_masked(self, M, v, mask, op_mult, op_add, op_select, init, early_exit=False):
+        return torch.from_numpy(self.orc.mxv_masked(self.INT, op_mult, op_add, op_select, M.Ap, M.Aj, M.Ax, v.numpy(), mask.numpy(), init,
+                                                    early_exit).astype(np.int32))
+
+    def v_count_mf(self, v, fill):
+        return self.orc.v_count_mf_dense(self.INT, v.numpy(), fill)
+
+    def dense_to_coo(self, dense, fill):
+        idx = torch.nonzero(dense != fill).flatten()
+        return idx.to(torch.int32), dense[idx]
+
+    def coo_to_dense(self, n, fill, vi, vx):
+        d = torch.full((n,), fill, dtype=vx.dtype)
+        d[vi.long()] = vx
+        return d
+
+
+def _bfs_reference(n, Ap, Aj, source):
+    depth = np.zeros(n, dtype=np.int32)
+    depth[source] = 1
+    front, level = [source], 1
+    while front:
+        level += 1
+        nxt = []
+        for u in front:
+            for k in range(Ap[u], Ap[u + 1]):
+                j = Aj[k]
+                if depth[j] == 0:
+                    depth[j] = level
+                    nxt.append(j)
+        front = nxt
+    return depth
+
+
+def _bfs_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from spla_b200 import algorithms, graphs
+        from spla_b200 import dist as sd
+
+        be = _OracleBackend()
+        n, Ap, Aj = graphs.rmat(9, edge_factor=6, seed=11)
+        Ax = torch.ones(Aj.numel(), dtype=torch.int32)
+        shard = algorithms.make_bfs_shard(be, n, Ap, Aj, Ax, rank, world)
+        hAp, hAj = Ap.numpy(), Aj.numpy()
+        deg = np.diff(hAp)
+        sources = [int(np.argmax(deg)), int(np.nonzero(deg > 0)[0][0]), int(np.nonzero(deg == 0)[0][0]) if (deg == 0).any() else 0]
+        for src in sources:
+            want = _bfs_reference(n, hAp, hAj, src)
+            for mode, ff in (("push", 0.05), ("pull", 0.05), ("push_pull", 0.05), ("push_pull", 0.3)):
+                trace = []
+                mine = algorithms.bfs_dist(be, shard, src, mode=mode, front_factor=ff, trace=trace)
+                full = torch.zeros(n, dtype=torch.int32)
+                full[shard["w0"]:shard["w1"]] = mine
+                sd.allgather_windows(full, shard["bounds"])
+                assert np.array_equal(full.numpy(), want), f"bfs_dist {mode} ff={ff} from {src} differs from the sequential BFS"
+                if mode == "push_pull" and ff == 0.3 and src == sources[0]:
+                    assert {t[0] for t in trace} == {"push", "pull"}, trace  # both directions were exercised
+        open(os.path.join(out_dir, f"bfs_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_bfs_dist_matches_sequential_bfs(tmp_path, world):
+    mp.spawn(_bfs_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"bfs_ok{r}").exists() for r in range(world))
