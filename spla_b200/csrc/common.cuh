@@ -127,7 +127,7 @@ namespace splacu {
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------
@@ -150,6 +150,10 @@ namespace splacu {
         size_t    cap_pairs = 0, cap_offsets = 0;
         void*     sort_tmp = nullptr;
         size_t    cap_sort_tmp = 0;
+        // small-front scratch (launch-latency paths): touched-column list of the push expand [kSmallList], compacted feedback
+        // indices / values of the sparse eadd_fdb [2 * kSmallFront]
+        uint32_t* small        = nullptr;
+        bool      pend_small   = false;  // the pending emit reads the small-front scratch instead of the bitmap
         // pending emit state between *_begin and *_emit
         int       pending      = 0;      // 0 none, 1 vxm (acc/bitmap), 2 eadd_fdb sparse
         uint32_t  pend_n       = 0;      // length of the bitmap domain
@@ -159,6 +163,8 @@ namespace splacu {
         const uint32_t* pend_src = nullptr;
     };
 
+    static constexpr uint32_t kSmallFront = 8192;// frontier entries one CTA turns into offsets / filters in one launch
+    static constexpr uint32_t kSmallList  = 4096;// touched columns a single CTA sorts and emits
     int ws_reserve_vector(Workspace* ws, uint32_t n, cudaStream_t s);
     int ws_reserve_blocks(Workspace* ws, uint32_t n_blocks);
     int ws_reserve_selbits(Workspace* ws, uint32_t n);

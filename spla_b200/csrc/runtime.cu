@@ -31,8 +31,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
@@ -338,6 +338,7 @@ int splacu_workspace_create(splacu_workspace* out) {
     SPLACU_REQUIRE(out, "null handle pointer");
     Workspace* ws = new Workspace();
     cudaError_t e = cudaMalloc(&ws->d_scalars, 64 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ws->small, (size_t) (kSmallList + 2 * kSmallFront) * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost(&ws->h_scalars, 64 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ws->d_scalars, 0, 64 * sizeof(uint32_t));
     if (e != cudaSuccess) {
@@ -351,7 +352,7 @@ int splacu_workspace_create(splacu_workspace* out) {
 int splacu_workspace_destroy(splacu_workspace handle) {
     if (!handle) return SPLACU_OK;
     Workspace* ws = reinterpret_cast<Workspace*>(handle);
-    cudaFree(ws->acc); cudaFree(ws->bitmap); cudaFree(ws->sel_bits); cudaFree(ws->block_sums); cudaFree(ws->d_scalars);
+    cudaFree(ws->acc); cudaFree(ws->bitmap); cudaFree(ws->sel_bits); cudaFree(ws->block_sums); cudaFree(ws->d_scalars); cudaFree(ws->small);
     cudaFreeHost(ws->h_scalars);
     cudaFree(ws->keys_a); cudaFree(ws->keys_b); cudaFree(ws->vals_a); cudaFree(ws->vals_b); cudaFree(ws->offsets);
     cudaFree(ws->sort_tmp);

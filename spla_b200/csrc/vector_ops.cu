@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "ops.cuh"
 
+#include <cub/block/block_scan.cuh>
+
 namespace splacu {
 
     static constexpr int kBlock = 256;
@@ -279,6 +281,42 @@ namespace splacu {
             r[i]         = next;
             fdb[i]       = value_neq(prev, next) ? next : fdb_fill;
         }
+    }
+
+    // the same for nv <= kSmallFront in ONE launch of one CTA: update, flag, scan in shared memory, write the changed (index,
+    // new value) pairs in input order to the small-front scratch and their count to *d_count
+    template<typename T>
+    __global__ void __launch_bounds__(1024) eadd_fdb_sparse_small_kernel(int op, T* __restrict__ r, uint32_t nv, const uint32_t* __restrict__ vi,
+                                                                         const T* __restrict__ vx, uint32_t* __restrict__ out_i,
+                                                                         uint32_t* __restrict__ out_x, uint32_t* __restrict__ d_count) {
+        using BlockScan = cub::BlockScan<uint32_t, 1024>;
+        __shared__ typename BlockScan::TempStorage tmp;
+        constexpr int  kItems = kSmallFront / 1024;
+        uint32_t       flag[kItems], idx[kItems], val[kItems], pos[kItems];
+        const uint32_t base = threadIdx.x * kItems;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const uint32_t t = base + k;
+            flag[k] = 0u, idx[k] = 0u, val[k] = 0u;
+            if (t < nv) {
+                const uint32_t i    = vi[t];
+                const T        prev = r[i];
+                const T        next = bin_dynamic<T>(op, prev, vx[t]);
+                r[i]                = next;
+                flag[k]             = value_neq(prev, next) ? 1u : 0u;
+                idx[k]              = i;
+                val[k]              = to_bits(next);
+            }
+        }
+        uint32_t total;
+        BlockScan(tmp).ExclusiveSum(flag, pos, total);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k)
+            if (flag[k]) {
+                out_i[pos[k]] = idx[k];
+                out_x[pos[k]] = val[k];
+            }
+        if (threadIdx.x == 0) *d_count = total;
     }
 
     // sparse v (unique indices): r[vi[k]] = op(r[vi[k]], vx[k]); bit k of the bitmap = changed
@@ -554,7 +592,25 @@ int splacu_v_eadd_fdb_sparse_begin(int dtype, int op, void* d_r, uint32_t nv, co
     SPLACU_REQUIRE(ws->pending == 0, "workspace has a pending emit");
     if (nv == 0) return SPLACU_OK;
     SPLACU_REQUIRE(d_r && d_vi && d_vx, "null pointer");
-    int rc = ws_reserve_vector(ws, nv, s);
+    int rc;
+    ws->pend_small = nv <= kSmallFront && get_option(OPT_SMALL_FRONT);
+    if (ws->pend_small) {
+        rc = dispatch_dtype(dtype, [&](auto tag) {
+            using T = decltype(tag);
+            eadd_fdb_sparse_small_kernel<T><<<1, 1024, 0, s>>>(op, static_cast<T*>(d_r), nv, d_vi, static_cast<const T*>(d_vx), ws->small + kSmallList,
+                                                              ws->small + kSmallList + kSmallFront, ws->d_scalars);
+            SPLACU_LAUNCH_CHECK();
+            return 0;
+        });
+        if (rc) return rc;
+        rc = read_scalar0(ws, h_nf, s);
+        if (rc) return rc;
+        ws->pending    = 2;
+        ws->pend_n     = nv;
+        ws->pend_count = *h_nf;
+        return SPLACU_OK;
+    }
+    rc = ws_reserve_vector(ws, nv, s);
     if (rc) return rc;
     rc = dispatch_dtype(dtype, [&](auto tag) {
         using T = decltype(tag);
@@ -584,6 +640,13 @@ int splacu_v_eadd_fdb_sparse_emit(splacu_workspace handle, uint32_t* d_fi, void*
     SPLACU_REQUIRE(ws->pending == 2, "eadd_fdb_sparse_emit without matching begin");
     ws->pending = 0;
     SPLACU_REQUIRE(ws->pend_count == 0 || (d_fi && d_fx), "null output pointers");
+    if (ws->pend_small) {
+        if (ws->pend_count) {
+            SPLACU_CUDA(cudaMemcpyAsync(d_fi, ws->small + kSmallList, (size_t) ws->pend_count * 4, cudaMemcpyDeviceToDevice, s));
+            SPLACU_CUDA(cudaMemcpyAsync(d_fx, ws->small + kSmallList + kSmallFront, (size_t) ws->pend_count * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        return SPLACU_OK;
+    }
     // the emit kernel also clears the words it visits, so the scratch bitmap is all-zero again afterwards
     return bitmap_emit(ws, ws->bitmap, ws->pend_n, EMIT_INDIRECT, const_cast<uint32_t*>(ws->pend_src), ws->pend_vi, 0u, d_fi,
                        static_cast<uint32_t*>(d_fx), s);

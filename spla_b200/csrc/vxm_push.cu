@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "ops.cuh"
 
+#include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace splacu {
@@ -30,6 +32,64 @@ namespace splacu {
         for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nv; t += stride) {
             const uint32_t i = vi[t];
             deg[t]           = Ap[i + 1] - Ap[i];
+        }
+    }
+
+    // Small fronts (nv <= kSmallFront) are launch-latency bound: ONE CTA gathers the degrees, scans them in shared memory and
+    // clears the touched-column counter of the expand (instead of degree kernel + 3 scan launches).
+    __global__ void __launch_bounds__(1024) vxm_offsets_small_kernel(uint32_t nv, const uint32_t* __restrict__ vi, const uint32_t* __restrict__ Ap,
+                                                                     uint32_t* __restrict__ off /*[nv + 1]*/, uint32_t* __restrict__ counter) {
+        using BlockScan = cub::BlockScan<uint32_t, 1024>;
+        __shared__ typename BlockScan::TempStorage tmp;
+        constexpr int  kItems = kSmallFront / 1024;
+        uint32_t       d[kItems];
+        const uint32_t base = threadIdx.x * kItems;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const uint32_t t = base + k;
+            uint32_t       x = 0;
+            if (t < nv) {
+                const uint32_t i = vi[t];
+                x                = Ap[i + 1] - Ap[i];
+            }
+            d[k] = x;
+        }
+        uint32_t total;
+        BlockScan(tmp).ExclusiveSum(d, d, total);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k)
+            if (base + k < nv) off[base + k] = d[k];
+        if (threadIdx.x == 0) {
+            off[nv]  = total;
+            *counter = 0u;
+        }
+    }
+
+    // ... and when the expand touched <= kSmallList columns, one CTA sorts the list it left, emits (j, acc[j]) in ascending
+    // order and resets exactly that scratch (instead of two passes over the n-bit bitmap plus a scan).
+    __global__ void __launch_bounds__(1024) vxm_emit_small_kernel(const uint32_t* __restrict__ list, uint32_t nr, uint32_t* __restrict__ acc,
+                                                                  uint32_t* __restrict__ bitmap, uint32_t identity, int end_bit,
+                                                                  uint32_t* __restrict__ ri, uint32_t* __restrict__ rx) {
+        constexpr int kItems = kSmallList / 1024;
+        using BlockSort     = cub::BlockRadixSort<uint32_t, 1024, kItems>;
+        __shared__ typename BlockSort::TempStorage tmp;
+        uint32_t key[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const uint32_t q = threadIdx.x * kItems + k;
+            key[k]           = q < nr ? list[q] : 0xffffffffu;
+        }
+        BlockSort(tmp).Sort(key, 0, end_bit);// only the bits a column id has (the padding sorts last: stable, all-ones digits); blocked arrangement: thread t holds ranks t * kItems .. t * kItems + kItems - 1
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const uint32_t q = threadIdx.x * kItems + k;
+            if (q < nr) {
+                const uint32_t j = key[k];
+                ri[q]            = j;
+                rx[q]            = acc[j];
+                acc[j]           = identity;
+                bitmap[j >> 5]   = 0u;// every set bit of the word is in the list, so all of them are being reset
+            }
         }
     }
 
@@ -55,7 +115,8 @@ namespace splacu {
                                                                     const T* __restrict__ vx, const T* __restrict__ mask,
                                                                     const uint32_t* __restrict__ sel_bits, const uint32_t* __restrict__ off /*[nv+1]*/,
                                                                     T* __restrict__ acc, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ keys,
-                                                                    T* __restrict__ vals, uint32_t invalid_key, uint32_t identity_bits) {
+                                                                    T* __restrict__ vals, uint32_t invalid_key, uint32_t identity_bits,
+                                                                    uint32_t* __restrict__ counter, uint32_t* __restrict__ list) {
         const uint32_t total = off[nv];
         const uint32_t chunk = kBlock * kEpt;
         for (uint64_t base = (uint64_t) blockIdx.x * chunk; base < total; base += (uint64_t) gridDim.x * chunk) {
@@ -82,7 +143,14 @@ namespace splacu {
                     if (take) {
                         const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&acc[j]);
                         atomic_combine<T>(sr.add_op(), &acc[j], sr.mult(x, Ax[k]), from_bits<T>(cur));
-                        if (cur == identity_bits) atomicOr(&bitmap[j >> 5], 1u << (j & 31u));
+                        if (cur == identity_bits) {
+                            const uint32_t bit = 1u << (j & 31u);
+                            const uint32_t old = atomicOr(&bitmap[j >> 5], bit);
+                            if (counter && !(old & bit)) {// first touch of column j: count it, remember it while the list has room
+                                const uint32_t pos = atomicAdd(counter, 1u);
+                                if (pos < kSmallList) list[pos] = j;
+                            }
+                        }
                     }
                 } else {
                     keys[e] = take ? j : invalid_key;
@@ -153,11 +221,18 @@ namespace splacu {
         if ((rc = ws_reserve_pairs(ws, 0, (size_t) nv + 1))) return rc;
 
         // 1. load-balancing offsets
-        vxm_degrees_kernel<<<grid_for(nv, kBlock, 8), kBlock, 0, s>>>(nv, d_vi, M->Ap, ws->offsets);
-        SPLACU_LAUNCH_CHECK();
-        if ((rc = scan_exclusive_u32(ws, ws->offsets, ws->offsets, nv, ws->offsets + nv, s))) return rc;
+        const bool fast  = fast_path_ok(op_mult, op_add);
+        const bool small = fast && nv <= kSmallFront && get_option(OPT_SMALL_FRONT);
+        uint32_t*  counter = small ? ws->d_scalars : nullptr;// the result count of a small front comes from the expand itself
+        if (small) {
+            vxm_offsets_small_kernel<<<1, 1024, 0, s>>>(nv, d_vi, M->Ap, ws->offsets, counter);
+            SPLACU_LAUNCH_CHECK();
+        } else {
+            vxm_degrees_kernel<<<grid_for(nv, kBlock, 8), kBlock, 0, s>>>(nv, d_vi, M->Ap, ws->offsets);
+            SPLACU_LAUNCH_CHECK();
+            if ((rc = scan_exclusive_u32(ws, ws->offsets, ws->offsets, nv, ws->offsets + nv, s))) return rc;
+        }
 
-        const bool fast     = fast_path_ok(op_mult, op_add);
         const T    identity = fast ? add_identity<T>(op_add) : from_bits<T>(ws->acc_identity);
         T*         acc      = reinterpret_cast<T*>(ws->acc);
         const int  grid     = sm_count() * 8;
@@ -179,7 +254,7 @@ namespace splacu {
             rc = dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
                 using S = decltype(sr);
                 vxm_expand_kernel<T, S, 0><<<grid, kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vi, d_vx, d_mask,
-                                                                   sel_bits, ws->offsets, acc, ws->bitmap, nullptr, nullptr, 0u, to_bits(identity));
+                                                                   sel_bits, ws->offsets, acc, ws->bitmap, nullptr, nullptr, 0u, to_bits(identity), counter, ws->small);
                 SPLACU_LAUNCH_CHECK();
                 return 0;
             });
@@ -197,7 +272,7 @@ namespace splacu {
                 sr.ident = T(0);
                 vxm_expand_kernel<T, SemiringDynamic<T>, 1><<<grid, kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vi, d_vx,
                                                                                    d_mask, nullptr, ws->offsets, nullptr, nullptr, ws->keys_a,
-                                                                                   reinterpret_cast<T*>(ws->vals_a), n, 0u);
+                                                                                   reinterpret_cast<T*>(ws->vals_a), n, 0u, nullptr, nullptr);
                 SPLACU_LAUNCH_CHECK();
                 int end_bit = 1;
                 while (end_bit < 32 && (n >> end_bit) != 0u) ++end_bit;// keys are in [0, n]
@@ -218,10 +293,12 @@ namespace splacu {
         }
 
         // 3. count
-        if ((rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;
+        if (!small && (rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;
         SPLACU_CUDA(cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, 4, cudaMemcpyDeviceToHost, s));
         SPLACU_CUDA(cudaStreamSynchronize(s));
         *h_nr             = ws->h_scalars[0];
+        ws->pend_small    = small && *h_nr <= kSmallList;
+        if (small && !ws->pend_small && (rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;// block offsets for the bitmap emit
         ws->pending       = 1;
         ws->pend_n        = n;
         ws->pend_count    = *h_nr;
@@ -267,6 +344,14 @@ int splacu_vxm_masked_emit(splacu_workspace wsh, uint32_t* d_ri, void* d_rx, voi
     ws->pending = 0;
     if (ws->pend_count == 0) return SPLACU_OK;// nothing touched: scratch still clean
     SPLACU_REQUIRE(d_ri && d_rx, "null output pointers");
+    if (ws->pend_small) {
+        int end_bit = 1;
+        while (end_bit < 32 && ((ws->pend_n - 1u) >> end_bit) != 0u) ++end_bit;
+        vxm_emit_small_kernel<<<1, 1024, 0, resolve_stream(stream)>>>(ws->small, ws->pend_count, ws->acc, ws->bitmap, ws->pend_identity, end_bit, d_ri,
+                                                                      static_cast<uint32_t*>(d_rx));
+        SPLACU_LAUNCH_CHECK();
+        return SPLACU_OK;
+    }
     return bitmap_emit(ws, ws->bitmap, ws->pend_n, EMIT_ACC_RESET, ws->acc, nullptr, ws->pend_identity, d_ri, static_cast<uint32_t*>(d_rx),
                        resolve_stream(stream));
 }

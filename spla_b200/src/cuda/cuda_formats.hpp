@@ -43,12 +43,17 @@ namespace spla {
         CudaBuffer(const CudaBuffer&)            = delete;
         CudaBuffer& operator=(const CudaBuffer&) = delete;
 
-        /** make room for `count` 4-byte elements; contents are NOT preserved when the buffer grows */
+        /** make room for `count` 4-byte elements; contents are NOT preserved when the buffer grows. Growth is geometric: a
+         *  traversal front that gains a few entries per step (a grid wave front) must not pay a cudaFree + cudaMalloc -- an
+         *  implicit device synchronisation -- on every step */
         void reserve(std::size_t count) {
             if (count <= m_capacity && m_ptr) return;
+            std::size_t want = m_capacity + m_capacity / 2;
+            if (want < count) want = count;
+            if (want < 256) want = 256;
             release();
-            SPLACU_CALL(splacu_malloc(&m_ptr, count * 4));
-            m_capacity = count;
+            SPLACU_CALL(splacu_malloc(&m_ptr, want * 4));
+            m_capacity = want;
         }
         void release() {
             if (m_ptr) splacu_free(m_ptr);
