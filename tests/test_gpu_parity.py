@@ -522,3 +522,36 @@ def test_pull_tail_ranges_widen_to_fit(backend):
         backend.set_option("mxv_phases", 4)
         backend.set_option("mxv_hub_min_count", 16)
         backend.set_option("mxv_tail_range_log2", 24)
+
+
+@pytest.mark.parametrize("small", [1, 0])
+def test_small_front_paths(backend, oracle, small):
+    """Fronts of <= 8192 entries take single-CTA offset / sorted-emit / filter kernels (option small_front, on by default);
+    the general kernels must give the same, bit for bit: push products whose result fits the 4096-entry list, overflows it,
+    and fronts above the limit; the sparse eadd_fdb below and above the limit; scratch reuse across calls."""
+    rng = np.random.default_rng(2024 + small)
+    n = 30000
+    Ap, Aj, Ax = cases.rand_csr(rng, FLOAT, n, n, 6, skew=False, kind="positive")
+    try:
+        backend.set_option("small_front", small)
+        M = make_csr(backend, n, n, Ap, Aj, Ax)
+        dist = np.full(n, np.float32(3.0e38), dtype=np.float32)
+        d_dev = to_dev(dist, backend)
+        for nv in (1, 40, 500, 3000, 8192, 8193, 20000, 7):
+            vi, vx = cases.rand_frontier(rng, FLOAT, n, nv, "positive")
+            mask = cases.rand_values(rng, FLOAT, n)
+            for om, oa, osel in (("MULT", "PLUS", "EQZERO"), ("PLUS", "MIN", "ALWAYS")):  # the last one (exact) feeds the eadd_fdb below
+                wi, wx = oracle.vxm_masked(FLOAT, om, oa, osel, Ap, Aj, Ax, n, vi, vx, mask)
+                gi, gx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(mask, backend), om, oa, osel)
+                backend.sync()
+                assert np.array_equal(to_np(gi, np.uint32), wi), f"vxm pattern nv={nv} {om}/{oa} small_front={small}"
+                assert_values(to_np(gx, np.float32), wx, cases.exact_expected(FLOAT, om, oa), what=f"vxm nv={nv} {om}/{oa}")
+            # the SSSP step: distances <- min(distances, candidates); feedback = the entries that improved, in index order
+            want_r, want_fi, want_fx = oracle.v_eadd_fdb_sparse(FLOAT, "MIN", dist, wi, wx)
+            fi, fx = backend.v_eadd_fdb_sparse(d_dev, gi, gx, "MIN")
+            backend.sync()
+            assert np.array_equal(to_np(fi, np.uint32), want_fi) and np.array_equal(to_np(fx, np.float32), want_fx), f"eadd_fdb feedback nv={nv}"
+            assert np.array_equal(to_np(d_dev, np.float32), want_r), f"eadd_fdb distances nv={nv}"
+            dist = want_r
+    finally:
+        backend.set_option("small_front", 1)
