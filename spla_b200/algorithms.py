@@ -115,9 +115,25 @@ def make_bfs_shard(be, n, Ap, Aj, Ax, rank, world):
     w0, w1 = b[rank], b[rank + 1]
     rAp, rAj, rAx = sd.row_slice(Ap, Aj, Ax, w0, w1)
     cAp, cAj, cAx = sd.column_slice(Ap, Aj, Ax, w0, w1)
-    return {"n": n, "bounds": b, "rank": rank, "world": world, "w0": w0, "w1": w1,
-            "M_rows": be.csr(w1 - w0, n, rAp, rAj.to(torch.int32), rAx),
+    # the dense frontier of the pull levels lives in the padded equal-window layout (dist.padded_layout): the uneven windows are
+    # then all-gathered by ONE collective instead of one broadcast per owner; the row slice's column ids are mapped once
+    if world > 1:
+        W, shifts = sd.padded_layout(b)
+        rAj = sd.to_padded_index(rAj, b, shifts)
+        n_vec = world * W
+    else:
+        W, n_vec = n, n
+    return {"n": n, "bounds": b, "rank": rank, "world": world, "w0": w0, "w1": w1, "W": W, "n_vec": n_vec,
+            "M_rows": be.csr(w1 - w0, n_vec, rAp, rAj.to(torch.int32), rAx),
             "M_cols": be.csr(n, w1 - w0, cAp, cAj, cAx)}
+
+
+def _owner(bounds, vertex):
+    """rank whose window [bounds[p], bounds[p+1]) holds the vertex"""
+    for p in range(len(bounds) - 1):
+        if bounds[p] <= vertex < bounds[p + 1]:
+            return p
+    raise ValueError("vertex outside the matrix")
 
 
 def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None, trace=None):
@@ -127,27 +143,31 @@ def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None,
     vxm_masked (push) or mxv_masked with early exit (pull), then the front size -- with one exchange step in between:
       push  all-gather of the sparse frontier pieces (dist.exchange_frontier); every rank expands the whole frontier against its
             column slice under its own window of the depth vector as the mask; results are disjoint windows
-      pull  all-gather of the dense frontier windows (dist.allgather_windows); every rank pulls its rows
-    and a 1-element all-reduce for the global front size, which every rank uses for the same push / pull decision."""
+      pull  ONE all-gather of the dense frontier windows in the padded layout (dist.allgather_padded); every rank pulls its rows
+    and an all-gather of the per-rank front sizes: their sum drives the same push / pull decision on every rank, and the sizes
+    themselves spare the next push level the count exchange of its frontier all-gather."""
     import contextlib
 
     import torch.distributed as tdist
 
     from . import dist as sd
 
-    n, b, rank = shard["n"], shard["bounds"], shard["rank"]
+    n, b, rank, world = shard["n"], shard["bounds"], shard["rank"], shard["world"]
     w0, w1 = shard["w0"], shard["w1"]
     n_loc = w1 - w0
+    W, p0 = shard["W"], (shard["rank"] * shard["W"] if shard["world"] > 1 else 0)
     dev = be.device
     ctx = torch.cuda.stream(be.stream) if getattr(be, "stream", None) is not None else contextlib.nullcontext()
     with ctx:
         depth = torch.zeros(n_loc, dtype=torch.int32, device=dev)
-        full = torch.zeros(n, dtype=torch.int32, device=dev)
+        full = torch.zeros(shard["n_vec"], dtype=torch.int32, device=dev)  # padding stays 0: no column id points at it
         own = w0 <= source < w1
         li = torch.tensor([source - w0] if own else [], dtype=torch.int32, device=dev)
         front = Frontier(be, n_loc, 0, coo=(li, torch.ones(li.numel(), dtype=torch.int32, device=dev)))
         size, level = 1, 1
+        sizes = [int(p == _owner(b, source)) for p in range(world)]  # per-rank sizes of the current frontier pieces
         cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        cnts = torch.zeros(world, dtype=torch.int64, device=dev)
         while size:
             if front.coo is not None:
                 if front.coo[0].numel():
@@ -156,7 +176,7 @@ def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None,
                 be.v_assign_masked(depth, front.dense, level, "SECOND", "NQZERO")
             push = mode == "push" or (mode == "push_pull" and size / n <= front_factor)
             if push:
-                vi, vx = sd.exchange_frontier(*front.as_coo(), w0, group=group)
+                vi, vx = sd.exchange_frontier(*front.as_coo(), w0, group=group, sizes=sizes if front.coo is not None else None)
                 if n_loc and vi.numel():
                     ri, rx = be.vxm_masked(shard["M_cols"], vi, vx, depth, "BAND", "BOR", "EQZERO")
                 else:
@@ -164,17 +184,21 @@ def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None,
                 front = Frontier(be, n_loc, 0, coo=(ri, rx))
             else:
                 if n_loc:
-                    full[w0:w1].copy_(front.as_dense())
-                sd.allgather_windows(full, b, group=group)
+                    full[p0:p0 + n_loc].copy_(front.as_dense())
+                if world > 1:
+                    sd.allgather_padded(full, W, group=group)
                 if n_loc:
                     r = be.mxv_masked(shard["M_rows"], full, depth, "BAND", "BOR", "EQZERO", 0, early_exit=True)
                 else:
                     r = depth[:0]
                 front = Frontier(be, n_loc, 0, dense=r)
             cnt[0] = front.count() if n_loc else 0
-            if shard["world"] > 1:
-                tdist.all_reduce(cnt, group=group)
-            size = int(cnt.item())
+            if world > 1:
+                tdist.all_gather_into_tensor(cnts, cnt, group=group)
+                sizes = [int(c) for c in cnts.tolist()]
+            else:
+                sizes = [int(cnt.item())]
+            size = sum(sizes)
             if trace is not None:
                 trace.append(("push" if push else "pull", size))
             level += 1

@@ -146,19 +146,22 @@ class PeerVector:
             self.handle.barrier(channel=0)
 
 
-def exchange_frontier(vi_local, vx_local, offset, group=None):
+def exchange_frontier(vi_local, vx_local, offset, group=None, sizes=None):
     """All-gather of sparse frontier pieces. Each rank contributes (indices local to its window + offset, values);
     returns the concatenated global (vi, vx), sorted because windows are disjoint and ordered by rank.
-    Pieces are uneven: counts are exchanged first, then the pieces travel padded to the largest one."""
+    Pieces are uneven: counts are exchanged first (unless the caller already knows every rank's `sizes`, as a traversal does
+    from the all-gather of the front sizes that ends its previous level), then the pieces travel padded to the largest one."""
     world = dist.get_world_size(group)
     vi_g = vi_local + offset if offset else vi_local
     if world == 1:
         return vi_g, vx_local
     dev = vi_local.device
-    cnt = torch.tensor([vi_local.numel()], dtype=torch.int64, device=dev)
-    cnts = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(cnts, cnt, group=group)
-    sizes = [int(c) for c in cnts.tolist()]
+    if sizes is None:
+        cnt = torch.tensor([vi_local.numel()], dtype=torch.int64, device=dev)
+        cnts = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(cnts, cnt, group=group)
+        sizes = [int(c) for c in cnts.tolist()]
+    assert sizes[dist.get_rank(group)] == vi_local.numel()
     cap = max(max(sizes), 1)
     send = torch.zeros(2 * cap, dtype=torch.int32, device=dev)  # [0, cap): indices, [cap, 2 cap): value bit patterns
     send[:vi_g.numel()] = vi_g.to(torch.int32)
