@@ -177,6 +177,11 @@ SPLACU_API int splacu_v_assign_masked_dense(int dtype, int op_assign, int op_sel
 SPLACU_API int splacu_v_assign_masked_sparse(int dtype, int op_assign, int op_select,
                                              void* d_r, uint32_t nm, const uint32_t* d_mi, const void* d_mx,
                                              uint32_t value_bits, void* stream);
+/* structure-only form of a dense vector, for the frontier exchange of a multi-GPU traversal ("all-gather an n-bit
+ * bitmap", 2 MB instead of 64 MB at scale 24): bit i of d_bits = op_select(v[i]) (ceil(n / 32) words, trailing bits 0), and back:
+ * out[i] = bit i ? one_bits : zero_bits. No reference counterpart (the reference is single-device). */
+SPLACU_API int splacu_v_pack_bits(int dtype, int op_select, uint32_t n, const void* d_v, uint32_t* d_bits, void* stream);
+SPLACU_API int splacu_v_unpack_bits(uint32_t n, const uint32_t* d_bits, uint32_t one_bits, uint32_t zero_bits, void* d_out, void* stream);
 /* number of entries != fill; reference src/cpu/cpu_v_count_mf.hpp:91-107, kernels/count.cl:46. Synchronises. */
 SPLACU_API int splacu_v_count_mf_dense(int dtype, uint32_t n, const void* d_v, uint32_t fill_bits,
                                        splacu_workspace ws, uint32_t* h_count, void* stream);

@@ -105,7 +105,7 @@ def pagerank(be, M, alpha=0.85, eps=1e-6, max_iter=1000):
 
 # ---------------------------------------------------------------------------------------------------------
 # Multi-GPU BFS (BASELINE config 4): one process per GPU, vertices owned in contiguous nnz-balanced windows.
-def make_bfs_shard(be, n, Ap, Aj, Ax, rank, world):
+def make_bfs_shard(be, n, Ap, Aj, Ax, rank, world, bitmap_exchange=False):
     """Rank `rank`'s share of a SYMMETRIC n x n matrix: window [b[rank], b[rank+1]) of the vertices (nnz-balanced on Ap, and --
     the matrix being symmetric -- on the columns too), M_rows = M[window, :] for the pull direction (row-sharded mxv)
     and M_cols = M[:, window] for the push direction (column-sharded vxm)."""
@@ -123,7 +123,11 @@ def make_bfs_shard(be, n, Ap, Aj, Ax, rank, world):
         n_vec = world * W
     else:
         W, n_vec = n, n
-    return {"n": n, "bounds": b, "rank": rank, "world": world, "w0": w0, "w1": w1, "W": W, "n_vec": n_vec,
+    # all stored values 1 (an adjacency matrix): BAND / BOR frontiers then only hold 0 / 1 and CAN travel as an n-bit bitmap
+    # (SURVEY 8e). Opt-in: on 2 B200s over NVLink the 64 MB dense all-gather is as fast as pack + 2 MB all-gather + unpack
+    # (3.07 ms against 3.33 / 3.63 ms per RMAT-24 BFS, tools/bench_bfs_dist.py --ab); not measured at 8 GPUs.
+    unit = bool(bitmap_exchange) and bool((Ax == 1).all().item())
+    return {"n": n, "bounds": b, "rank": rank, "world": world, "w0": w0, "w1": w1, "W": W, "n_vec": n_vec, "unit_values": unit,
             "M_rows": be.csr(w1 - w0, n_vec, rAp, rAj.to(torch.int32), rAx),
             "M_cols": be.csr(n, w1 - w0, cAp, cAj, cAx)}
 
@@ -143,7 +147,9 @@ def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None,
     vxm_masked (push) or mxv_masked with early exit (pull), then the front size -- with one exchange step in between:
       push  all-gather of the sparse frontier pieces (dist.exchange_frontier); every rank expands the whole frontier against its
             column slice under its own window of the depth vector as the mask; results are disjoint windows
-      pull  ONE all-gather of the dense frontier windows in the padded layout (dist.allgather_padded); every rank pulls its rows
+      pull  ONE all-gather of the dense frontier windows in the padded layout (dist.allgather_padded) -- optionally as an n-bit
+            bitmap when the matrix holds only ones (make_bfs_shard(bitmap_exchange=True); 2 MB instead of 64 MB at scale 24,
+            SURVEY 8e); every rank pulls its rows
     and an all-gather of the per-rank front sizes: their sum drives the same push / pull decision on every rank, and the sizes
     themselves spare the next push level the count exchange of its frontier all-gather."""
     import contextlib
@@ -161,6 +167,8 @@ def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None,
     with ctx:
         depth = torch.zeros(n_loc, dtype=torch.int32, device=dev)
         full = torch.zeros(shard["n_vec"], dtype=torch.int32, device=dev)  # padding stays 0: no column id points at it
+        as_bits = world > 1 and shard["unit_values"]  # W is a multiple of 32: every window starts on a bitmap word
+        bits = torch.zeros(shard["n_vec"] // 32, dtype=torch.int32, device=dev) if as_bits else None
         own = w0 <= source < w1
         li = torch.tensor([source - w0] if own else [], dtype=torch.int32, device=dev)
         front = Frontier(be, n_loc, 0, coo=(li, torch.ones(li.numel(), dtype=torch.int32, device=dev)))
@@ -183,10 +191,16 @@ def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None,
                     ri, rx = vi[:0], vx[:0]
                 front = Frontier(be, n_loc, 0, coo=(ri, rx))
             else:
-                if n_loc:
-                    full[p0:p0 + n_loc].copy_(front.as_dense())
-                if world > 1:
-                    sd.allgather_padded(full, W, group=group)
+                if as_bits:
+                    if n_loc:
+                        be.pack_bits(front.as_dense(), "NQZERO", out=bits[p0 // 32:p0 // 32 + (n_loc + 31) // 32])
+                    sd.allgather_padded(bits, W // 32, group=group)
+                    be.unpack_bits(bits, shard["n_vec"], 1, 0, out=full)
+                else:
+                    if n_loc:
+                        full[p0:p0 + n_loc].copy_(front.as_dense())
+                    if world > 1:
+                        sd.allgather_padded(full, W, group=group)
                 if n_loc:
                     r = be.mxv_masked(shard["M_rows"], full, depth, "BAND", "BOR", "EQZERO", 0, early_exit=True)
                 else:

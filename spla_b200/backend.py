@@ -36,6 +36,7 @@ SYMBOLS = [
     "splacu_vxm_masked_begin", "splacu_vxm_masked_emit", "splacu_vxm_masked",
     "splacu_coo_to_dense", "splacu_dense_to_coo_count", "splacu_dense_to_coo_emit",
     "splacu_v_assign_masked_dense", "splacu_v_assign_masked_sparse", "splacu_v_count_mf_dense",
+    "splacu_v_pack_bits", "splacu_v_unpack_bits",
     "splacu_v_eadd_fdb_dense", "splacu_v_eadd_fdb_sparse_begin", "splacu_v_eadd_fdb_sparse_emit",
     "splacu_v_eadd_dense", "splacu_v_reduce_dense",
 ]
@@ -77,6 +78,7 @@ def load_library(build_if_missing=True):
         "splacu_v_assign_masked_dense": [i32, i32, i32, u32, vp, vp, u32, vp],
         "splacu_v_assign_masked_sparse": [i32, i32, i32, vp, u32, vp, vp, u32, vp],
         "splacu_v_count_mf_dense": [i32, u32, vp, u32, vp, pu32, vp],
+        "splacu_v_pack_bits": [i32, i32, u32, vp, vp, vp], "splacu_v_unpack_bits": [u32, vp, u32, u32, vp, vp],
         "splacu_v_eadd_fdb_dense": [i32, i32, u32, vp, vp, vp, u32, vp],
         "splacu_v_eadd_fdb_sparse_begin": [i32, i32, vp, u32, vp, vp, vp, pu32, vp],
         "splacu_v_eadd_fdb_sparse_emit": [vp, vp, vp, vp],
@@ -269,6 +271,22 @@ class Backend:
         code = dtype_code(v)
         self._check(self.lib.splacu_v_count_mf_dense(code, v.numel(), _ptr(v), scalar_bits(code, fill), self.ws, C.byref(self._nr), self.stream_ptr))
         return self._nr.value
+
+    def pack_bits(self, v, op_select, out=None):
+        """bit i = op_select(v[i]) (int32 words, ceil(n / 32) of them): the structure-only form a frontier is exchanged in"""
+        n = v.numel()
+        if out is None:
+            out = self.empty((n + 31) // 32, dtype=torch.int32)
+        assert out.numel() >= (n + 31) // 32 and out.dtype == torch.int32
+        self._check(self.lib.splacu_v_pack_bits(dtype_code(v), SEL[op_select], n, _ptr(v), _ptr(out), self.stream_ptr))
+        return out
+
+    def unpack_bits(self, bits, n, one, zero, out):
+        """out[i] = bit i ? one : zero"""
+        code = dtype_code(out)
+        assert out.numel() >= n and bits.numel() >= (n + 31) // 32
+        self._check(self.lib.splacu_v_unpack_bits(n, _ptr(bits), scalar_bits(code, one), scalar_bits(code, zero), _ptr(out), self.stream_ptr))
+        return out
 
     def v_eadd_fdb_dense(self, r, v, op, fdb_fill, fdb=None):
         code = dtype_code(r)

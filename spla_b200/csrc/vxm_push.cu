@@ -183,6 +183,12 @@ namespace splacu {
         }
     }
 
+    __global__ void __launch_bounds__(kBlock) unpack_bits_kernel(const uint32_t* __restrict__ bits, uint32_t n, uint32_t one, uint32_t zero,
+                                                                uint32_t* __restrict__ out) {
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = ((bits[i >> 5] >> (i & 31u)) & 1u) ? one : zero;
+    }
+
     // exact path: after the stable sort, the head of every key run folds its run left to right
     template<typename T>
     __global__ void __launch_bounds__(kBlock) vxm_fold_runs_kernel(int op_add, uint32_t n_pairs, const uint32_t* __restrict__ keys,
@@ -311,6 +317,30 @@ namespace splacu {
 using namespace splacu;
 
 extern "C" {
+
+int splacu_v_pack_bits(int dtype, int op_select, uint32_t n, const void* d_v, uint32_t* d_bits, void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(op_select >= 0 && op_select < SPLACU_SELOP_COUNT, "unknown op_select");
+    if (n == 0) return SPLACU_OK;
+    SPLACU_REQUIRE(d_v && d_bits, "null pointer");
+    const Select sel = make_select(op_select);
+    cudaStream_t s   = resolve_stream(stream);
+    return dispatch_dtype(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        select_bits_kernel<T><<<grid_for(n, kBlock, 8), kBlock, 0, s>>>(sel, static_cast<const T*>(d_v), n, d_bits);
+        SPLACU_LAUNCH_CHECK();
+        return 0;
+    });
+}
+
+int splacu_v_unpack_bits(uint32_t n, const uint32_t* d_bits, uint32_t one_bits, uint32_t zero_bits, void* d_out, void* stream) {
+    SPLACU_CHECK_INIT();
+    if (n == 0) return SPLACU_OK;
+    SPLACU_REQUIRE(d_bits && d_out, "null pointer");
+    unpack_bits_kernel<<<grid_for(n, kBlock, 8), kBlock, 0, resolve_stream(stream)>>>(d_bits, n, one_bits, zero_bits, static_cast<uint32_t*>(d_out));
+    SPLACU_LAUNCH_CHECK();
+    return SPLACU_OK;
+}
 
 int splacu_vxm_masked_begin(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select,
                             uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,

@@ -149,6 +149,20 @@ class _OracleBackend:
     def v_count_mf(self, v, fill):
         return self.orc.v_count_mf_dense(self.INT, v.numpy(), fill)
 
+    def pack_bits(self, v, op_select, out=None):
+        assert op_select == "NQZERO"
+        words = np.packbits((v.numpy() != 0).astype(np.uint8), bitorder="little")
+        words = np.concatenate([words, np.zeros((-len(words)) % 4, dtype=np.uint8)]).view(np.int32)
+        if out is None:
+            return torch.from_numpy(words.copy())
+        out[:len(words)] = torch.from_numpy(words.copy())
+        return out
+
+    def unpack_bits(self, bits, n, one, zero, out):
+        b = np.unpackbits(bits.numpy().view(np.uint8), bitorder="little")[:n]
+        out[:n] = torch.from_numpy(np.where(b != 0, one, zero).astype(np.int32))
+        return out
+
     def dense_to_coo(self, dense, fill):
         idx = torch.nonzero(dense != fill).flatten()
         return idx.to(torch.int32), dense[idx]
@@ -187,14 +201,16 @@ def _bfs_worker(rank, world, port, out_dir):
         be = _OracleBackend()
         n, Ap, Aj = graphs.rmat(9, edge_factor=6, seed=11)
         Ax = torch.ones(Aj.numel(), dtype=torch.int32)
-        shard = algorithms.make_bfs_shard(be, n, Ap, Aj, Ax, rank, world)
+        shards = [algorithms.make_bfs_shard(be, n, Ap, Aj, Ax, rank, world, bitmap_exchange=flag) for flag in (False, True)]
+        assert [s["unit_values"] for s in shards] == [False, True]
         hAp, hAj = Ap.numpy(), Aj.numpy()
         deg = np.diff(hAp)
         sources = [int(np.argmax(deg)), int(np.nonzero(deg > 0)[0][0]), int(np.nonzero(deg == 0)[0][0]) if (deg == 0).any() else 0]
         for src in sources:
             want = _bfs_reference(n, hAp, hAj, src)
-            for mode, ff in (("push", 0.05), ("pull", 0.05), ("push_pull", 0.05), ("push_pull", 0.3)):
+            for k, (mode, ff) in enumerate((("push", 0.05), ("pull", 0.05), ("push_pull", 0.05), ("push_pull", 0.3), ("pull", 0.05))):
                 trace = []
+                shard = shards[k & 1]  # dense int32 and bitmap exchange of the pull levels alternate; "pull" runs with both
                 mine = algorithms.bfs_dist(be, shard, src, mode=mode, front_factor=ff, trace=trace)
                 full = torch.zeros(n, dtype=torch.int32)
                 full[shard["w0"]:shard["w1"]] = mine

@@ -555,3 +555,22 @@ def test_small_front_paths(backend, oracle, small):
             dist = want_r
     finally:
         backend.set_option("small_front", 1)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 70001])
+def test_pack_unpack_bits(backend, n):
+    """Structure-only exchange form of a dense vector: bit i = select(v[i]), trailing bits of the last word 0, and back."""
+    rng = np.random.default_rng(n)
+    for dtype, np_t in ((INT, np.int32), (FLOAT, np.float32)):
+        v = (rng.integers(-1, 2, n)).astype(np_t)
+        for osel, pred in (("NQZERO", v != 0), ("GTZERO", v > 0), ("ALWAYS", np.ones(n, bool))):
+            bits = backend.pack_bits(to_dev(v, backend), osel)
+            backend.sync()
+            got = bits.cpu().numpy().view(np.uint8)
+            want = np.packbits(pred.astype(np.uint8), bitorder="little")
+            want = np.concatenate([want, np.zeros((-len(want)) % 4, dtype=np.uint8)])
+            assert np.array_equal(got, want), (n, dtype, osel)
+            out = to_dev(np.full(n, 9, dtype=np_t), backend)
+            backend.unpack_bits(bits, n, 1, 0, out)
+            backend.sync()
+            assert np.array_equal(to_np(out, np_t), pred.astype(np_t)), (n, dtype, osel)

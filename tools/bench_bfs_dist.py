@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--sources", type=int, default=16)
     ap.add_argument("--front-factor", type=float, default=0.05)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--bitmap", action="store_true", help="pull levels exchange the frontier as an n-bit bitmap (opt-in)")
+    ap.add_argument("--ab", action="store_true", help="time the pull levels with the bitmap exchange and with the dense int32 exchange")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -64,7 +66,7 @@ def main():
     result = {"n_gpus": world}
     if args.check:
         n, Ap, Aj, ones = build(16)
-        shard = algorithms.make_bfs_shard(be, n, Ap, Aj, ones, rank, world)
+        shard = algorithms.make_bfs_shard(be, n, Ap, Aj, ones, rank, world, bitmap_exchange=args.bitmap)
         M = be.csr(n, n, Ap.to(torch.int32), Aj, ones)
         deg = Ap[1:] - Ap[:-1]
         ok = True
@@ -83,7 +85,7 @@ def main():
     nnz = int(Aj.numel())
     deg = Ap[1:] - Ap[:-1]
     t0 = time.perf_counter()
-    shard = algorithms.make_bfs_shard(be, n, Ap, Aj, ones, rank, world)
+    shard = algorithms.make_bfs_shard(be, n, Ap, Aj, ones, rank, world, bitmap_exchange=args.bitmap or args.ab)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     srcs = pick_sources(deg, args.sources, 11)
@@ -93,6 +95,25 @@ def main():
     del Ap, Aj, ones, deg
     torch.cuda.empty_cache()
     algorithms.bfs_dist(be, shard, srcs[0], front_factor=args.front_factor)  # warm-up (NCCL channels, allocator)
+    if args.ab:
+        unit = shard["unit_values"]
+        ab = {}
+        for name, flag in (("bitmap", unit), ("dense_int32", False), ("bitmap_again", unit)):
+            shard["unit_values"] = flag
+            algorithms.bfs_dist(be, shard, srcs[0], front_factor=args.front_factor)
+            ts = []
+            for s in srcs:
+                barrier()
+                t0 = time.perf_counter()
+                algorithms.bfs_dist(be, shard, s, mode="push_pull", front_factor=args.front_factor)
+                barrier()
+                dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                ts.append(float(dt.item()) * 1e3)
+            ts.sort()
+            ab[name] = {"ms_mean": sum(ts) / len(ts), "ms_median": ts[len(ts) // 2], "ms_min": ts[0]}
+        shard["unit_values"] = args.bitmap
+        result["pull_exchange_ab"] = ab
     times, teps, traces = [], [], []
     for s in srcs:
         trace = []
