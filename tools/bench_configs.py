@@ -87,7 +87,7 @@ def config1(be, out):
         gm = float(torch.tensor(teps).log().mean().exp().item())
         res[mode] = {"sources": len(srcs), "ms_mean": sum(ms) / len(ms), "gteps_geomean": gm / 1e9}
     out["config1_bfs_rmat16"] = {"n": n, "nnz": int(Aj.numel()), "front_factor": 0.05, "modes": res,
-                                 "bound": "launch / host-sync latency (7-9 levels of ~10 launches and one 4-byte read each)"}
+                                 "bound": "launch / host-sync latency (7-9 levels of a handful of launches and one 4-byte read each)"}
 
 
 def config2(be, out, peak):
