@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_util import idx_dev, to_dev, to_np
+from gpu_util import assert_values, idx_dev, to_dev, to_np
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -46,7 +46,7 @@ def test_pagerank_matches_reference_ranks(backend):
     z = np.load(os.path.join(GOLDEN, "algorithms_reference.npz"))
     n, M = golden_matrix(backend, z, z["pr_values"])
     p, iters = algorithms.pagerank(backend, M, 0.85, 1e-6)
-    np.testing.assert_allclose(to_np(p, np.float32), z["pr"], rtol=1e-5, atol=1e-5 * float(np.abs(z["pr"]).max()))
+    assert_values(to_np(p, np.float32), z["pr"], False, what=f"pr() golden, {iters} iterations")  # strict 1e-5 relative per element
 
 
 def test_bfs_properties_rmat20(backend):

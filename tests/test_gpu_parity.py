@@ -16,7 +16,7 @@ import torch
 import cases
 import known_answers
 from cases import FLOAT, INT, UINT
-from gpu_util import assert_values, idx_dev, make_csr, to_dev, to_np
+from gpu_util import assert_values, idx_dev, make_csr, mxv_bound, np_select, to_dev, to_np, vxm_bound
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -63,10 +63,12 @@ def test_golden_reference_outputs(backend):
         p = f"c{cid}_"
         exact = cases.exact_expected(dtype, om, oa) or ee
         r = run_mxv(backend, dtype, om, oa, osel, n_cols, z[p + "Ap"], z[p + "Aj"], z[p + "Ax"], z[p + "v"], z[p + "mask_r"], z[p + "init"][0], ee)
-        assert_values(r, z[p + "r"], exact, what=f"mxv case {cid} {om}/{oa}/{osel} ee={ee}")
+        assert_values(r, z[p + "r"], exact, what=f"mxv case {cid} {om}/{oa}/{osel} ee={ee}",
+                      bound=lambda: mxv_bound(om, oa, z[p + "Ap"], z[p + "Aj"], z[p + "Ax"], z[p + "v"], z[p + "init"][0]))
         ri, rx = run_vxm(backend, dtype, om, oa, osel, n_cols, z[p + "Ap"], z[p + "Aj"], z[p + "Ax"], z[p + "vi"], z[p + "vx"], z[p + "mask_c"])
         assert np.array_equal(ri, z[p + "ri"]), f"vxm pattern case {cid} {om}/{oa}/{osel}"
-        assert_values(rx, z[p + "rx"], cases.exact_expected(dtype, om, oa), what=f"vxm case {cid} {om}/{oa}/{osel}")
+        assert_values(rx, z[p + "rx"], cases.exact_expected(dtype, om, oa), what=f"vxm case {cid} {om}/{oa}/{osel}",
+                      bound=lambda: vxm_bound(om, oa, z[p + "Ap"], z[p + "Aj"], z[p + "Ax"], n_cols, z[p + "vi"], z[p + "vx"], np_select(osel, z[p + "mask_c"]), ri))
         n += 1
     assert n >= 100
 
@@ -96,7 +98,8 @@ def test_all_op_pairs_vs_oracle(backend, oracle, dtype):
             want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, ee)
             got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init, early_exit=ee)
             backend.sync()
-            assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa) or ee, what=f"mxv {om}/{oa}/{osel} ee={ee}")
+            assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa) or ee, what=f"mxv {om}/{oa}/{osel} ee={ee}",
+                          bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
 
             vi, vx = cases.rand_frontier(rng, dtype, n_rows, 97, vk)
             maskc = cases.rand_values(rng, dtype, n_cols)
@@ -104,7 +107,8 @@ def test_all_op_pairs_vs_oracle(backend, oracle, dtype):
             gi, gx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(maskc, backend), om, oa, osel)
             backend.sync()
             assert np.array_equal(to_np(gi, np.uint32), wi), f"vxm pattern {om}/{oa}/{osel}"
-            assert_values(to_np(gx, cases.NP[dtype]), wx, cases.exact_expected(dtype, om, oa), what=f"vxm {om}/{oa}/{osel}")
+            assert_values(to_np(gx, cases.NP[dtype]), wx, cases.exact_expected(dtype, om, oa), what=f"vxm {om}/{oa}/{osel}",
+                          bound=lambda: vxm_bound(om, oa, Ap, Aj, Ax, n_cols, vi, vx, np_select(osel, maskc), wi))
     assert k > 100
 
 
@@ -125,7 +129,8 @@ def test_named_semirings_shapes(backend, oracle, dtype, om, oa, osel, shape):
         want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, ee)
         got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init, early_exit=ee)
         backend.sync()
-        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa) or ee, what=f"mxv ee={ee}")
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa) or ee, what=f"mxv {om}/{oa} {shape} ee={ee}",
+                      bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
     for nv in (0, 1, max(1, n_rows // 50), n_rows):
         vi, vx = cases.rand_frontier(rng, dtype, n_rows, nv, kind)
         maskc = cases.rand_values(rng, dtype, n_cols)
@@ -133,7 +138,8 @@ def test_named_semirings_shapes(backend, oracle, dtype, om, oa, osel, shape):
         gi, gx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(maskc, backend), om, oa, osel)
         backend.sync()
         assert np.array_equal(to_np(gi, np.uint32), wi), f"vxm pattern nv={nv}"
-        assert_values(to_np(gx, cases.NP[dtype]), wx, cases.exact_expected(dtype, om, oa), what=f"vxm nv={nv}")
+        assert_values(to_np(gx, cases.NP[dtype]), wx, cases.exact_expected(dtype, om, oa), what=f"vxm {om}/{oa} {shape} nv={nv}",
+                      bound=lambda: vxm_bound(om, oa, Ap, Aj, Ax, n_cols, vi, vx, np_select(osel, maskc), wi))
 
 
 @pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "MULT", "PLUS", "EQZERO"), (UINT, "BAND", "BOR", "ALWAYS"), (FLOAT, "MULT", "PLUS", "ALWAYS"),
@@ -175,7 +181,8 @@ def test_pull_hub_cache_forced(backend, oracle, dtype, om, oa, osel, hub_smem, h
         want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
         got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
         backend.sync()
-        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"hub mxv rep {rep}")
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"hub mxv rep {rep}",
+                      bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
 
 
 def _skewed_csr(rng, dtype, n_rows, n_cols, kind, avg=30):
@@ -225,7 +232,8 @@ def test_pull_column_class_phases_forced(backend, oracle, dtype, om, oa, osel, s
         want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
         got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
         backend.sync()
-        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"phases mxv rep {rep}")
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"phases mxv rep {rep}",
+                      bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
     # early exit and non-associative adds keep using the original CSR of the handle
     v = cases.rand_values(rng, dtype, n_cols, kind)
     mask = cases.rand_values(rng, dtype, n_rows)
@@ -261,7 +269,8 @@ def test_pull_column_class_phases_auto(backend, oracle):
         want = oracle.mxv_masked(dtype, om, oa, osel, Ap, cols, Ax, v, mask, 1, False)
         got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, 1)
         backend.sync()
-        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"auto phases {dtype}")
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"auto phases {dtype}",
+                      bound=lambda: mxv_bound(om, oa, Ap, cols, Ax, v, 1))
 
 
 def test_edge_cases(backend, oracle):
@@ -460,7 +469,8 @@ def test_pull_column_classes_csr_format(backend, oracle, dtype, om, oa, osel):
     want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, 2, False)
     got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, 2)
     backend.sync()
-    assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what="csr-format classes")
+    assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what="csr-format classes",
+                  bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, 2))
 
 
 @pytest.mark.parametrize("seg", [1, 0])
@@ -499,7 +509,8 @@ def test_pull_tail_column_ranges(backend, oracle, dtype, om, oa, osel, seg):
         want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
         got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
         backend.sync()
-        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"tail ranges rep {rep}")
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"tail ranges rep {rep}",
+                      bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
 
 
 def test_pull_tail_ranges_widen_to_fit(backend):

@@ -142,3 +142,33 @@ def test_live_differential_vs_reference(oracle):
                 assert np.array_equal(ai, bi) and np.array_equal(ax.view(np.uint32), bx.view(np.uint32)), (dtype, om, oa, osel)
                 checked += 1
     assert checked > 500
+
+
+def test_float_bound_helpers_against_oracle(oracle):
+    """tests/gpu_util.py's escape for cancelling float sums: its fp32 restatement of the binary ops agrees with the C oracle bit for
+    bit, and the sequential reference fold itself lies inside the derived any-order summation bound around the float64 sum."""
+    from gpu_util import mxv_bound, np_binop_f32, np_select, vxm_bound
+
+    rng = np.random.default_rng(5)
+    a = cases.rand_values(rng, FLOAT, 400)
+    b = cases.rand_values(rng, FLOAT, 400, "positive")
+    for op in cases.BIN_OPS:
+        if not cases.op_valid(FLOAT, op):
+            continue
+        got = np_binop_f32(op, a, b)
+        want = np.array([oracle.binary(FLOAT, op, x, y) for x, y in zip(a, b)], dtype=np.float32)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), op
+    n_rows, n_cols = 300, 200
+    Ap, Aj, Ax = cases.rand_csr(rng, FLOAT, n_rows, n_cols, 12, skew=True)
+    v = cases.rand_values(rng, FLOAT, n_cols)
+    mask = np.ones(n_rows, np.float32)
+    for om in ("MULT", "PLUS", "MINUS", "MIN"):
+        r = oracle.mxv_masked(FLOAT, om, "PLUS", "ALWAYS", Ap, Aj, Ax, v, mask, np.float32(0.25), False)
+        exact, ab = mxv_bound(om, "PLUS", Ap, Aj, Ax, v, np.float32(0.25))
+        assert (np.abs(r.astype(np.float64) - exact) <= ab + 1e-12 * np.abs(exact)).all(), om
+        vi, vx = cases.rand_frontier(rng, FLOAT, n_rows, 60)
+        maskc = cases.rand_values(rng, FLOAT, n_cols)
+        ri, rx = oracle.vxm_masked(FLOAT, om, "PLUS", "EQZERO", Ap, Aj, Ax, n_cols, vi, vx, maskc)
+        exact, ab = vxm_bound(om, "PLUS", Ap, Aj, Ax, n_cols, vi, vx, np_select("EQZERO", maskc), ri)
+        assert (np.abs(rx.astype(np.float64) - exact) <= ab + 1e-12 * np.abs(exact)).all(), om
+    assert mxv_bound("MULT", "MIN", Ap, Aj, Ax, v, 0) is None
