@@ -40,8 +40,13 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=24, help="RMAT scale of the workload (BASELINE metric: 24)")
     ap.add_argument("--edge-factor", type=int, default=16)
-    ap.add_argument("--cpu-scale", type=int, default=20, help="RMAT scale of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample-nnz", type=int, default=64 << 20, help="entries of the bounded CPU-baseline sample (leading row block of the SAME graph)")
     ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: CPU seconds the steps may take in total; the sample is the whole "
+                                                                      "graph when it fits, else the leading row block that does")
+    ap.add_argument("--no-vxm", action="store_true", help="skip the push (vxm) block of the line")
+    ap.add_argument("--no-bfs", action="store_true", help="skip the BFS push-pull block (BASELINE config 4) of the line")
+    ap.add_argument("--bfs-sources", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time vxm / BFS-semiring variants (reported under 'extra')")
     return ap.parse_args()
@@ -149,27 +154,43 @@ def make_graph(scale, edge_factor, device):
     return n, Ap, Aj, Ax
 
 
-def cpu_reference_run(args, steps, warmup):
-    """The reference's own CPU implementation of the path (oracle/_ref, else the C port) on a bounded sample:
-    RMAT scale `--cpu-scale` from the same generator, same ops. Returns (gteps, seconds_per_step, info)."""
+CPU_GTEPS_GUESS = 0.15  # spla's CPU backend on one core, for sizing the bounded sample (measured 0.18-0.19 on the pool's hosts)
+
+
+def cpu_reference_run(args, steps, warmup, graph=None, max_nnz=None):
+    """The reference's own CPU implementation of the path (oracle/_ref, else the C port) on a bounded sample of the SAME workload:
+    the leading row block [0, r) of the same RMAT scale-`--scale` matrix (all n columns kept, the full-length v), r chosen so that
+    the block holds <= max_nnz entries -- the whole graph when it fits. Returns (gteps, seconds_per_step, info)."""
     import numpy as np
     import torch
 
     from oracle import oracle as orc
 
-    dev = "cuda" if torch.cuda.is_available() else "cpu"
-    n, Ap, Aj, Ax = make_graph(args.cpu_scale, args.edge_factor, dev)
-    Ap_h = Ap.cpu().numpy().astype(np.uint32)
-    Aj_h = Aj.cpu().numpy().astype(np.uint32)
-    Ax_h = Ax.cpu().numpy().astype(np.float32)
-    nnz = len(Aj_h)
+    if graph is None:
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        graph = make_graph(args.scale, args.edge_factor, dev)
+    n, Ap, Aj, Ax = graph
+    nnz_all = int(Aj.numel())
+    if max_nnz is None or max_nnz >= nnz_all:
+        r = n
+    else:
+        r = int(torch.searchsorted(Ap.to(torch.int64).contiguous(), torch.tensor([max_nnz], device=Ap.device, dtype=torch.int64), right=True).item()) - 1
+        r = max(1, min(n, r))
+    nnz = int(Ap[r].item())
+    Ap_h = Ap[:r + 1].cpu().numpy().astype(np.uint32)
+    Aj_h = Aj[:nnz].cpu().numpy().astype(np.uint32)
+    Ax_h = Ax[:nnz].cpu().numpy().astype(np.float32)
     v = np.full(n, 1.0 / n, dtype=np.float32)
-    mask = np.ones(n, dtype=np.float32)
-    sample = f"RMAT scale-{args.cpu_scale} ef{args.edge_factor} (n={n}, nnz={nnz}), same generator/ops, {steps} timed calls after {warmup} warm-up"
+    mask = np.ones(r, dtype=np.float32)
+    whole = r == n
+    sample = (f"{'the whole' if whole else 'leading row block [0, %d) of the' % r} RMAT scale-{args.scale} ef{args.edge_factor} matrix of the GPU arm "
+              f"({r} x {n}, nnz={nnz} of {nnz_all}), same generator / seed / ops, {steps} timed calls after {warmup} warm-up")
     if orc.ref_available():
         ref = orc.RefSpla()
-        rows = np.repeat(np.arange(n, dtype=np.uint32), np.diff(Ap_h.astype(np.int64)))
-        M = ref.matrix(orc.FLOAT, n, n, rows, Aj_h, Ax_h)
+        rows = np.repeat(np.arange(r, dtype=np.uint32), np.diff(Ap_h.astype(np.int64)))
+        t0 = time.perf_counter()
+        M = ref.matrix(orc.FLOAT, r, n, rows, Aj_h, Ax_h)
+        build_s = time.perf_counter() - t0
         del rows
         for _ in range(max(0, warmup - 1)):
             ref.mxv_masked(M, *OPS, v, mask, 0.0)
@@ -177,6 +198,7 @@ def cpu_reference_run(args, steps, warmup):
         kind = "reference"
     else:
         o = orc.Oracle()
+        build_s = 0.0
         for _ in range(warmup):
             o.mxv_masked(orc.FLOAT, *OPS, Ap_h, Aj_h, Ax_h, v, mask, 0.0)
         t0 = time.perf_counter()
@@ -184,20 +206,28 @@ def cpu_reference_run(args, steps, warmup):
             o.mxv_masked(orc.FLOAT, *OPS, Ap_h, Aj_h, Ax_h, v, mask, 0.0)
         sec = (time.perf_counter() - t0) / steps
         kind = "port"
-    return nnz / sec / 1e9, sec, {"kind": kind, "cores": 1, "host_cores_total": os.cpu_count(), "sample": sample}
+    return nnz / sec / 1e9, sec, {"kind": kind, "cores": 1, "host_cores_total": os.cpu_count(), "sample": sample, "sample_rows": r, "sample_nnz": nnz,
+                                  "whole_graph": whole, "matrix_build_s": round(build_s, 2)}
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    gteps, sec, info = cpu_reference_run(args, args.steps, args.warmup)
+    total = args.steps + max(1, args.warmup)
+    max_nnz = int(args.ref_budget_s * CPU_GTEPS_GUESS * 1e9 / total)
+    gteps, sec, info = cpu_reference_run(args, args.steps, max(1, args.warmup), max_nnz=max_nnz)
+    cfg = workload_config(args, world=1)
+    cfg["parallelism"] = "spla CPU backend, one host thread (the reference has no multi-threaded or multi-device path)"
+    cfg["sample"] = info["sample"]
+    cfg["same_config"] = bool(info["whole_graph"])
     line = {
-        "impl": "reference", "metric": METRIC, "value": gteps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": gteps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, args.warmup),
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world=args.gpus),
+        "config": cfg,
         "cpu_baseline": dict(info, value=gteps, unit=UNIT),
         "e2e": {"value": gteps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "spla's CPU backend is single-threaded (reference src/cpu/cpu_mxv.hpp:53); each step is one exec_mxv_masked on the bounded sample",
+        "note": "spla's CPU backend is single-threaded (reference src/cpu/cpu_mxv.hpp:53); each step is one exec_mxv_masked over the sample named in "
+                "config.sample (GTEPS = its entries / its time; the per-entry cost of a row block equals the whole graph's)",
     }
     print(json.dumps(line), flush=True)
 
@@ -235,8 +265,8 @@ def main():
     r0, r1 = bounds[rank], bounds[rank + 1]
     Ap_l, Aj_l, Ax_l = sd.row_slice(Ap, Aj, Ax, r0, r1)
     nnz_l = int(Aj_l.numel())
-    del Ap, Aj, Ax
-    torch.cuda.empty_cache()
+    del Ax
+    torch.cuda.empty_cache()  # Ap / Aj (the structure, 2 GB at scale 24) stay for the vxm / BFS blocks
     # N > 1: the vector lives in the padded layout of spla_b200.dist (equal windows, rank p at [p*W, p*W + rows_p)), so that a step
     # ends with one in-place all-gather; the column ids of the local slice are mapped once. N = 1: w0 = 0, n_vec = n.
     if world > 1:
@@ -333,15 +363,51 @@ def main():
             dist.all_reduce(t)
             kernel_ms_ranks = [round(float(x), 4) for x in t.tolist()]
 
-        # ---- e2e: the C-ABI call with HOST buffers (pinned h2d of v and the mask window, d2h of the result window) ----
+        # ---- parity of the timed path at this N: one step from the canonical input v = 1/n; the sum of the result over all ranks
+        #      against a float64 re-computation that does not depend on N or on the kernel: sum_i (A v)_i = (sum of all Ax) / n ----
+        a.fill_(1.0 / n)
+        b.zero_()  # the padding of the windows stays 0 on every rank
+        step(a, b)
+        be.sync()
+        sums = torch.stack([b[w0:w1].double().sum(), Ax_l.double().sum() / n,
+                            (b[:w0].double().sum() + b[w1:].double().sum()) if world > 1 else torch.zeros((), dtype=torch.float64, device=dev)])
+        if world > 1:
+            part = sums[:2].clone()
+            dist.all_reduce(part)
+            # after the all-gather every rank holds every window: the foreign windows must add up to the other ranks' partial sums
+            gathered_ok = abs(float(sums[0] + sums[2]) - float(part[0])) <= 1e-9 * abs(float(part[0]))
+            sums = torch.stack([part[0], part[1], sums[2]])
+        else:
+            gathered_ok = True
+        got_sum, want_sum = float(sums[0]), float(sums[1])
+        parity_rel = abs(got_sum - want_sum) / abs(want_sum)
+        parity_ok = parity_rel <= 1e-6 and gathered_ok
+        if world > 1:
+            flag = torch.tensor([1.0 if parity_ok else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            parity_ok = bool(flag.item() == 1.0)
+        assert parity_ok, f"bench parity check failed at N={world}: sum(r) = {got_sum!r}, float64 expectation {want_sum!r} (rel {parity_rel:.3e}), gathered_ok={gathered_ok}"
+
+        # ---- e2e: the C-ABI call with HOST buffers (pinned h2d of the rank's window of v and of its mask window, d2h of its result window;
+        #      at N > 1 the uploaded windows are all-gathered over NVLink, so the job as a whole uploads v once, not N times) ----
         hv = torch.full((n_vec,), 1.0 / n, dtype=torch.float32).pin_memory()
         hm = torch.ones(r1 - r0, dtype=torch.float32).pin_memory()
         hr = torch.empty(r1 - r0, dtype=torch.float32).pin_memory()
         lib, sp = be.lib, be.stream_ptr
         e2e_steps = max(3, min(args.steps, 10))
 
+        nw = r1 - r0  # this rank's window
+
+        def upload_v(dst, stream_ptr):
+            if world == 1:
+                lib.splacu_memcpy_h2d(C.c_void_p(dst.data_ptr()), C.c_void_p(hv.data_ptr()), n_vec * 4, stream_ptr)
+            else:
+                lib.splacu_memcpy_h2d(C.c_void_p(dst[w0:w1].data_ptr()), C.c_void_p(hv[w0:w1].data_ptr()), nw * 4, stream_ptr)
+
         def e2e_step():
-            lib.splacu_memcpy_h2d(C.c_void_p(a.data_ptr()), C.c_void_p(hv.data_ptr()), n_vec * 4, sp)
+            upload_v(a, sp)
+            if world > 1:
+                sd.allgather_padded(a, W)
             lib.splacu_memcpy_h2d(C.c_void_p(mask_l.data_ptr()), C.c_void_p(hm.data_ptr()), (r1 - r0) * 4, sp)
             rc = lib.splacu_mxv_masked(M.handle, FLOAT, BIN[OPS[0]], BIN[OPS[1]], SEL[OPS[2]], C.c_void_p(a.data_ptr()), C.c_void_p(mask_l.data_ptr()),
                                        C.c_void_p(b[w0:w1].data_ptr()), scalar_bits(FLOAT, 0.0), 0, sp)
@@ -376,10 +442,12 @@ def main():
                 q = k & 1
                 if k >= 2:
                     s_in.wait_event(ev_k[q])    # the kernels of step k-2 have consumed dv[q] / dm[q]
-                lib.splacu_memcpy_h2d(C.c_void_p(dv[q].data_ptr()), C.c_void_p(hv.data_ptr()), n_vec * 4, p_in)
+                upload_v(dv[q], p_in)
                 lib.splacu_memcpy_h2d(C.c_void_p(dm[q].data_ptr()), C.c_void_p(hm.data_ptr()), (r1 - r0) * 4, p_in)
                 ev_in[q].record(s_in)
                 be.stream.wait_event(ev_in[q])
+                if world > 1:
+                    sd.allgather_padded(dv[q], W)
                 if k >= 2:
                     be.stream.wait_event(ev_out[q])  # dr[q] of step k-2 has been downloaded
                 rc = lib.splacu_mxv_masked(M.handle, FLOAT, BIN[OPS[0]], BIN[OPS[1]], SEL[OPS[2]], C.c_void_p(dv[q].data_ptr()),
@@ -398,19 +466,37 @@ def main():
         e2e_pipelined(pipe_steps)
         t_e2e = max_over_ranks((time.perf_counter() - t0) / pipe_steps)
         assert torch.equal(hrs[0], hr) and torch.equal(hrs[1], hr), "pipelined e2e result differs from the serial one"
-        h2d = (n_vec + (r1 - r0)) * 4
-        d2h = (r1 - r0) * 4
+        # whole-job bytes per step (all ranks): v once + every mask window up, every result window down
+        h2d = (n + n) * 4 if world > 1 else (n_vec + (r1 - r0)) * 4
+        d2h = n * 4
         checksum = float(hr.double().sum())
 
         extra = None
         if args.extra and world == 1:
             extra = extra_timings(be, M, n, nnz, args.steps)
 
+    # ---- the other half of the metric: push (vxm) at two frontier sizes, N = 1; BFS push-pull (BASELINE config 4) at every N ----
+    vxm = bfs = None
+    if world == 1 and not (args.no_vxm and args.no_bfs):
+        ones = torch.ones(nnz, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        Mi = be.csr(n, n, Ap.to(torch.int32), Aj, ones)
+        if not args.no_vxm:
+            vxm = vxm_block(be, Mi, n, Ap, max(3, args.steps // 2))
+        if not args.no_bfs:
+            bfs = bfs_block(be, args, n, Ap, Aj, ones, rank, world, single=Mi)
+        del Mi, ones
+    elif not args.no_bfs:
+        ones = torch.ones(nnz, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        bfs = bfs_block(be, args, n, Ap, Aj, ones, rank, world)
+        del ones
+
     # ---- CPU baseline: rank 0, N = 1 only ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            g, sec, info = cpu_reference_run(args, args.cpu_steps, 2)
+            g, sec, info = cpu_reference_run(args, args.cpu_steps, 2, graph=(n, Ap, Aj, Ax_l), max_nnz=args.cpu_sample_nnz)
             cpu = dict(info, value=g, unit=UNIT, ms_per_step=sec * 1e3)
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": f"failed: {ex}"}
@@ -446,13 +532,125 @@ def main():
                          "traffic": ncu_traffic(kernel_name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": ms_kernel, "kernel_ms_per_rank": kernel_ms_ranks, "note": ("rank-0 bytes, slowest rank's bandwidth; " if world > 1 else "") + roofline_note},
             "cpu_baseline": cpu,
+            "parity_checked": True,
+            "parity": {"sum_r_all_ranks": got_sum, "float64_expectation": want_sum, "rel_diff": parity_rel, "bar": 1e-6,
+                       "what": "one step from v = 1/n at this N: sum over all ranks of r against (sum of all Ax)/n in float64; at N > 1 also: the "
+                               "all-gathered foreign windows on every rank add up to the other ranks' partial sums; asserted before this line is printed. "
+                               "Per-element parity at this size: tests/test_gpu_baseline_configs.py (vs the reference CPU backend)"},
         }
+        if vxm:
+            line["vxm"] = vxm
+        if bfs:
+            line["bfs"] = bfs
         if extra:
             line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def vxm_alg_bytes(nv, e_f, n_cols, nr, reads_mask=True, reads_ax=True):
+    """8 nv [vi, vx] + 8 nv [Ap[i], Ap[i+1]] + 8 E_f [Aj + Ax; 4 E_f when Ax is provably not read] + 4 min(n_cols, E_f) S [mask] + 8 nr [ri, rx]."""
+    return 16 * nv + (8 if reads_ax else 4) * e_f + (4 * min(n_cols, e_f) if reads_mask else 0) + 8 * nr
+
+
+def vxm_block(be, Mi, n, Ap, reps):
+    """exec_vxm_masked INT BAND/BOR/EQZERO (the BFS push step, reference tests/test_vxm.cpp:140-187 shape) over random frontiers of 5 % and
+    1 % of the vertices of the bench graph, nothing visited yet (every reached column passes the mask and is a first touch)."""
+    import torch
+
+    dev = be.device
+    peak, _ = measured_peak()
+    g = torch.Generator(device=dev)
+    g.manual_seed(9)
+    deg = (Ap[1:] - Ap[:-1]).to(torch.int64)
+    out = {"ops": "INT BAND/BOR/EQZERO, frontier values 1, matrix values 1, mask all zero", "timing": "CUDA events on the backend's stream around "
+           f"{reps} whole splacu_vxm_masked calls (offsets, expand, count with its 4-byte host read, ordered emit)"}
+    ri = torch.empty(n, dtype=torch.int32, device=dev)
+    rx = torch.empty(n, dtype=torch.int32, device=dev)
+    visited = torch.zeros(n, dtype=torch.int32, device=dev)
+    for frac in (0.05, 0.01):
+        vi = torch.nonzero(torch.rand(n, generator=g, device=dev) < frac).flatten().to(torch.int32)
+        vx = torch.ones(vi.numel(), dtype=torch.int32, device=dev)
+        ef = int(deg[vi.long()].sum().item())
+        torch.cuda.synchronize()
+        with torch.cuda.stream(be.stream):
+            oi, _ = be.vxm_masked(Mi, vi, vx, visited, "BAND", "BOR", "EQZERO", out=(ri, rx))
+            nr = int(oi.numel())
+            be.sync()
+            l0 = be.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(be.stream)
+            for _ in range(reps):
+                be.vxm_masked(Mi, vi, vx, visited, "BAND", "BOR", "EQZERO", out=(ri, rx))
+            e1.record(be.stream)
+            be.sync()
+        ms = e0.elapsed_time(e1) / reps
+        info = be.vxm_info() if hasattr(be, "vxm_info") else {}
+        reads_ax = not info.get("struct_only", False)
+        bts = vxm_alg_bytes(int(vi.numel()), ef, n, nr, reads_mask=True, reads_ax=reads_ax)
+        ach = bts / (ms * 1e-3) / 1e9
+        out[f"front_{frac}"] = {"nv": int(vi.numel()), "edges": ef, "nr": nr, "ms": ms, "gteps": ef / ms / 1e6, "launches_per_call": (be.launch_count() - l0) / reps,
+                                "algorithmic_bytes": bts, "ax_read": reads_ax, "achieved_gbs": ach, "frac_of_measured_hbm_peak": ach / peak,
+                                "traffic": ncu_traffic(f"vxm_expand_kernel@{frac}")}
+    return out
+
+
+def bfs_block(be, args, n, Ap, Aj, ones, rank, world, single=None):
+    """BASELINE config 4: BFS push-pull (front_factor 0.05; INT BAND/BOR/EQZERO push, early-exit pull) on the bench graph from random
+    sources of non-zero degree; Graph500-style TEPS = entries of the reached rows / time, geometric mean over the sources. N = 1: the
+    reference's own call sequence on one handle (spla_b200.algorithms.bfs); N > 1: vertices owned in nnz-balanced windows, row slice for
+    the pull, column slice for the push, NCCL frontier exchange per level (algorithms.bfs_dist)."""
+    import torch
+    import torch.distributed as dist
+
+    from spla_b200 import algorithms
+
+    dev = be.device
+    deg = Ap[1:] - Ap[:-1]
+    gcpu = torch.Generator(device="cpu")
+    gcpu.manual_seed(11)
+    cand = torch.nonzero(deg > 0).flatten().cpu()
+    srcs = cand[torch.randperm(cand.numel(), generator=gcpu)[:max(1, args.bfs_sources)]].tolist()
+    if world > 1:
+        shard = algorithms.make_bfs_shard(be, n, Ap, Aj, ones, rank, world)
+        w0, w1 = shard["w0"], shard["w1"]
+        run = lambda s, trace=None: algorithms.bfs_dist(be, shard, s, mode="push_pull", front_factor=0.05, trace=trace)  # noqa: E731
+    else:
+        w0, w1 = 0, n
+        run = lambda s, trace=None: algorithms.bfs(be, single, s, mode="push_pull", front_factor=0.05, trace=trace)  # noqa: E731
+    deg_loc = deg[w0:w1]
+
+    def barrier():
+        be.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    run(srcs[0])  # warm-up (allocator, NCCL channels)
+    times, teps, trace0, reached0 = [], [], None, None
+    for k, src in enumerate(srcs):
+        trace = []
+        barrier()
+        t0 = time.perf_counter()
+        d = run(src, trace)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        e = deg_loc[d > 0].sum().to(torch.int64).reshape(1)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e)
+        times.append(float(dt.item()))
+        teps.append(float(e.item()) / float(dt.item()))
+        if k == 0:
+            trace0, reached0 = trace, int(e.item())
+    gm = float(torch.tensor(teps, dtype=torch.float64).log().mean().exp().item())
+    return {"config": "BASELINE config 4: BFS push-pull, front_factor 0.05, INT BAND/BOR/EQZERO, on the bench graph", "sources": len(srcs),
+            "gteps_geomean": gm / 1e9, "ms_mean": 1e3 * sum(times) / len(times), "ms_min": 1e3 * min(times), "levels_first_source": trace0,
+            "edges_reached_first_source": reached0,
+            "exchange": "none (single GPU)" if world == 1 else "per level: all-gather of the sparse frontier pieces (push) or of the dense windows (pull) + front sizes, NCCL",
+            "timing": "host wall clock between synchronize (+ barrier) pairs, max over ranks: a BFS is host-driven, one 4-byte read per level"}
 
 
 def extra_timings(be, M, n, nnz, steps):

@@ -184,7 +184,8 @@ def bfs_dist(be, shard, source, mode="push_pull", front_factor=0.05, group=None,
                 be.v_assign_masked(depth, front.dense, level, "SECOND", "NQZERO")
             push = mode == "push" or (mode == "push_pull" and size / n <= front_factor)
             if push:
-                vi, vx = sd.exchange_frontier(*front.as_coo(), w0, group=group, sizes=sizes if front.coo is not None else None)
+                had_coo = front.coo is not None  # the cached per-rank sizes describe a frontier that was produced sparse
+                vi, vx = sd.exchange_frontier(*front.as_coo(), w0, group=group, sizes=sizes if had_coo else None)
                 if n_loc and vi.numel():
                     ri, rx = be.vxm_masked(shard["M_cols"], vi, vx, depth, "BAND", "BOR", "EQZERO")
                 else:

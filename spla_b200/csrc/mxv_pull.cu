@@ -34,6 +34,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstring>
+#include <vector>
 
 namespace splacu {
 
@@ -384,12 +385,11 @@ namespace splacu {
         if (cap > n) cap = n;
         if (cap < 4) cap = 4;
         const uint32_t min_count = (uint32_t) get_option(OPT_MXV_HUB_MIN_COUNT);
-        uint32_t*      h_keys    = (uint32_t*) malloc((size_t) cap * 4);
-        HUB_CUDA(cudaMemcpyAsync(h_keys, keys_out, (size_t) cap * 4, cudaMemcpyDeviceToHost, s));
+        std::vector<uint32_t> h_keys(cap);
+        HUB_CUDA(cudaMemcpyAsync(h_keys.data(), keys_out, (size_t) cap * 4, cudaMemcpyDeviceToHost, s));
         HUB_CUDA(cudaStreamSynchronize(s));
         uint32_t n_hub = 0;
         while (n_hub < cap && ~h_keys[n_hub] >= min_count) ++n_hub;
-        free(h_keys);
         if (n_hub >= 64 || mode >= 2) {
             if (n_hub == 0) n_hub = cap < 4 ? cap : 4;
             HUB_CUDA(cudaMalloc(&M->hub_cols, (size_t) n_hub * 4));

@@ -306,7 +306,7 @@ int splacu_csr_create(splacu_csr* out, uint32_t n_rows, uint32_t n_cols, uint32_
     M->Ax     = static_cast<const uint32_t*>(d_Ax);
     int rc    = csr_build_metadata(M, resolve_stream(stream));
     if (rc != 0) {
-        delete M;
+        splacu_csr_destroy(reinterpret_cast<splacu_csr>(M));// frees whatever metadata was allocated before the failure
         return rc;
     }
     *out = reinterpret_cast<splacu_csr>(M);
