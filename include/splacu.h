@@ -53,7 +53,8 @@ enum {
     SPLACU_E_INVALID        = -1, /* bad argument (null pointer, unknown op, op not defined for dtype) */
     SPLACU_E_NOT_INIT       = -2, /* splacu_init not called / no CUDA device */
     SPLACU_E_CAPACITY       = -3, /* caller-provided output buffer too small; required size reported */
-    SPLACU_E_NOT_IMPLEMENTED = -4 /* user-defined (non built-in) op: no device code available */
+    SPLACU_E_NOT_IMPLEMENTED = -4, /* user-defined (non built-in) op and no NVRTC / driver library to compile it with */
+    SPLACU_E_COMPILE        = -5  /* user-defined op: its source text failed to compile (message in splacu_last_error) */
 };
 
 /* ---- runtime: replaces reference src/opencl/cl_accelerator.{hpp,cpp} (CLAccelerator::init,
@@ -72,7 +73,8 @@ SPLACU_API int         splacu_launch_count(uint64_t* count); /* kernels launched
  * src/opencl/cl_accelerator.cpp:84-175): "mxv_hub" 0 = off, 1 = auto (default), 2 = always build the hub cache of
  * the pull kernel; "mxv_hub_min_count" = references a column needs to earn a hub slot (default 16);
  * "mxv_hub_total" / "mxv_hub_smem" = hub slots in total / staged in shared memory; "mxv_l2_persist" = L2 persisting window
- * on v; "vxm_selbits" = expand large frontiers against a select(mask) bitmap instead of the mask itself */
+ * on v; "vxm_selbits" = expand large frontiers against a select(mask) bitmap instead of the mask itself; "vxm_struct" = structure-only
+ * push for large frontiers whose products are provably one value under an idempotent add (default 1) */
 SPLACU_API int         splacu_set_option(const char* name, int64_t value);
 SPLACU_API int         splacu_get_option(const char* name, int64_t* value);
 
@@ -129,6 +131,14 @@ SPLACU_API int splacu_mxv_masked(splacu_csr M, int dtype, int op_mult, int op_ad
 typedef struct splacu_workspace_t* splacu_workspace;
 SPLACU_API int splacu_workspace_create(splacu_workspace* ws);
 SPLACU_API int splacu_workspace_destroy(splacu_workspace ws);
+/* A workspace serves ONE call at a time: between *_begin and its *_emit no other call may use it (the pending state is checked),
+ * and calls that share a workspace or a matrix handle must be ordered on one stream -- the per-call scratch of a handle (selection
+ * bitmap, packed hub values, tile partials) is not re-entrant. splacu_workspace_reset drops a pending emit after an error between
+ * begin and emit (an exception in the caller) and marks the scratch dirty, so that the workspace stays usable. */
+SPLACU_API int splacu_workspace_reset(splacu_workspace ws, void* stream);
+/* introspection for tests / the bench: *struct_only = 1 when the last vxm call on this workspace took the structure-only path
+ * (uniform frontier values x uniform matrix values under an idempotent add: Ax, vx and the accumulator are never read) */
+SPLACU_API int splacu_workspace_info(splacu_workspace ws, int* struct_only);
 
 /* Push (SpMSpV): for every stored (i,x) of sparse v, for (j,a) in row i with select(mask[j]):
  *   acc[j] = first ? mult(x,a) : add(acc[j], mult(x,a));  result = touched (j, acc[j]) ascending in j.
@@ -199,6 +209,48 @@ SPLACU_API int splacu_v_eadd_dense(int dtype, int op, uint32_t n, void* d_r, con
  * and commutative (PLUS, MULT, MIN, MAX, LOR, LAND, BOR, BAND, BXOR); FLOAT PLUS/MULT differ by summation order. */
 SPLACU_API int splacu_v_reduce_dense(int dtype, int op, uint32_t n, const void* d_v, uint32_t init_bits,
                                      splacu_workspace ws, uint32_t* h_result_bits, void* stream);
+
+/* ---- user-defined ops -----------------------------------------------------------------------------
+ * The reference compiles the SOURCE TEXT of a user op, "(T a, T b) { ... }" (OpBinary::make_int/uint/float, OpSelect::make_*,
+ * reference src/op.cpp:294-342, e.g. tests/test_vector.cpp:299-302), into its OpenCL kernels at first use
+ * (src/opencl/cl_program_builder.cpp:65-120). Here an op is either a built-in (id >= 0: splacu_binop / splacu_selop, name and
+ * source ignored) or user-defined (id < 0: `name` = the op's name, `source` = its text in exactly that form; `uint` is defined).
+ * A call whose ops are all built-ins forwards to the ahead-of-time specialised entry point above. Otherwise the library compiles
+ * generic kernels for (dtype, mult, add, select) with NVRTC at first use (cached by name + source) and keeps the reference CPU
+ * backend's SEQUENTIAL semantics, since nothing is known about a user op: mxv folds a row strictly left to right (one thread per
+ * row, early exit included), vxm sorts the (column, product) pairs stably and folds every column left to right. Bit-exact
+ * against the CPU backend for any op (compiled with --fmad=false: mult and add round separately, as two std::function calls do).
+ * Errors: SPLACU_E_COMPILE (the text does not compile; splacu_last_error() carries the NVRTC log), SPLACU_E_NOT_IMPLEMENTED
+ * (no libnvrtc / libcuda on the machine). Never a CPU fallback.
+ * v_reduce with a user op is the one neighbour task without device code (a fold of n elements by an op of unknown associativity
+ * is sequential): the spla plug-in hands that task to spla's own CPU algorithm, exactly what Dispatcher::dispatch does for a key
+ * an accelerator does not provide (reference src/core/dispatcher.cpp:57-60). */
+typedef struct splacu_op {
+    int         id;     /* built-in id, or < 0 for a user-defined op */
+    const char* name;   /* user op: its name (part of the cache key) */
+    const char* source; /* user op: "(T a, T b) { ... }" / "(T a) { ... }" */
+} splacu_op;
+
+SPLACU_API int splacu_mxv_masked_ops(splacu_csr M, int dtype, const splacu_op* op_mult, const splacu_op* op_add, const splacu_op* op_select,
+                                     const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits, int early_exit, void* stream);
+/* emit with splacu_vxm_masked_emit */
+SPLACU_API int splacu_vxm_masked_begin_ops(splacu_csr M, int dtype, const splacu_op* op_mult, const splacu_op* op_add, const splacu_op* op_select,
+                                           uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
+                                           splacu_workspace ws, uint32_t* h_nr, void* stream);
+SPLACU_API int splacu_v_assign_masked_dense_ops(int dtype, const splacu_op* op_assign, const splacu_op* op_select, uint32_t n,
+                                                void* d_r, const void* d_mask, uint32_t value_bits, void* stream);
+SPLACU_API int splacu_v_assign_masked_sparse_ops(int dtype, const splacu_op* op_assign, const splacu_op* op_select,
+                                                 void* d_r, uint32_t nm, const uint32_t* d_mi, const void* d_mx, uint32_t value_bits, void* stream);
+SPLACU_API int splacu_v_eadd_dense_op(int dtype, const splacu_op* op, uint32_t n, void* d_r, const void* d_u, const void* d_v, void* stream);
+SPLACU_API int splacu_v_eadd_fdb_dense_op(int dtype, const splacu_op* op, uint32_t n, void* d_r, const void* d_v,
+                                          void* d_fdb, uint32_t fdb_fill_bits, void* stream);
+/* emit with splacu_v_eadd_fdb_sparse_emit */
+SPLACU_API int splacu_v_eadd_fdb_sparse_begin_op(int dtype, const splacu_op* op, void* d_r, uint32_t nv, const uint32_t* d_vi,
+                                                 const void* d_vx, splacu_workspace ws, uint32_t* h_nf, void* stream);
+/* compile the module for (dtype, mult, add, select) without running anything (needs no GPU: NVRTC cross-compiles for sm_100a);
+ * any op pointer may be NULL (= unused slot). *image_bytes = size of the device image. For tests and for warming the cache. */
+SPLACU_API int splacu_jit_compile(int dtype, const splacu_op* op_mult, const splacu_op* op_add, const splacu_op* op_select, size_t* image_bytes);
+SPLACU_API int splacu_jit_compile_count(uint64_t* count); /* modules compiled so far (cache misses) */
 
 #if defined(__cplusplus)
 }

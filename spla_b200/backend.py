@@ -32,14 +32,33 @@ SYMBOLS = [
     "splacu_malloc", "splacu_free", "splacu_malloc_host", "splacu_free_host",
     "splacu_memcpy_h2d", "splacu_memcpy_d2h", "splacu_memcpy_d2d", "splacu_fill", "splacu_publish_window",
     "splacu_csr_create", "splacu_csr_destroy", "splacu_mxv_masked",
-    "splacu_workspace_create", "splacu_workspace_destroy",
+    "splacu_workspace_create", "splacu_workspace_destroy", "splacu_workspace_reset", "splacu_workspace_info",
     "splacu_vxm_masked_begin", "splacu_vxm_masked_emit", "splacu_vxm_masked",
     "splacu_coo_to_dense", "splacu_dense_to_coo_count", "splacu_dense_to_coo_emit",
     "splacu_v_assign_masked_dense", "splacu_v_assign_masked_sparse", "splacu_v_count_mf_dense",
     "splacu_v_pack_bits", "splacu_v_unpack_bits",
     "splacu_v_eadd_fdb_dense", "splacu_v_eadd_fdb_sparse_begin", "splacu_v_eadd_fdb_sparse_emit",
     "splacu_v_eadd_dense", "splacu_v_reduce_dense",
+    "splacu_mxv_masked_ops", "splacu_vxm_masked_begin_ops", "splacu_v_assign_masked_dense_ops", "splacu_v_assign_masked_sparse_ops",
+    "splacu_v_eadd_dense_op", "splacu_v_eadd_fdb_dense_op", "splacu_v_eadd_fdb_sparse_begin_op", "splacu_jit_compile", "splacu_jit_compile_count",
 ]
+
+
+class Op(C.Structure):
+    """splacu_op: a built-in id, or id = -1 with (name, source text "(T a, T b) { ... }") of a user-defined op"""
+    _fields_ = [("id", C.c_int), ("name", C.c_char_p), ("source", C.c_char_p)]
+
+
+def make_op(op, table):
+    """'PLUS' -> built-in; ('my_plus', '(int a, int b) { return a + b + 1; }') -> user-defined (compiled with NVRTC at first use)"""
+    if isinstance(op, str):
+        return Op(table[op], None, None)
+    name, source = op
+    return Op(-1, name.encode(), source.encode())
+
+
+def _user(*ops):
+    return any(not isinstance(o, str) for o in ops)
 
 
 class SplacuError(RuntimeError):
@@ -56,6 +75,7 @@ def load_library(build_if_missing=True):
     lib = C.CDLL(path)
     vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
     pu32 = C.POINTER(C.c_uint32)
+    pop = C.POINTER(Op)
     sig = {
         "splacu_init": [i32], "splacu_finalize": [], "splacu_device_count": [C.POINTER(C.c_int)],
         "splacu_device_name": [C.c_char_p, i32], "splacu_sm_count": [C.POINTER(C.c_int)],
@@ -69,6 +89,7 @@ def load_library(build_if_missing=True):
         "splacu_csr_create": [C.POINTER(vp), u32, u32, u32, vp, vp, vp, vp], "splacu_csr_destroy": [vp],
         "splacu_mxv_masked": [vp, i32, i32, i32, i32, vp, vp, vp, u32, i32, vp],
         "splacu_workspace_create": [C.POINTER(vp)], "splacu_workspace_destroy": [vp],
+        "splacu_workspace_reset": [vp, vp], "splacu_workspace_info": [vp, C.POINTER(C.c_int)],
         "splacu_vxm_masked_begin": [vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, pu32, vp],
         "splacu_vxm_masked_emit": [vp, vp, vp, vp],
         "splacu_vxm_masked": [vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, vp, u32, pu32, vp, vp],
@@ -84,6 +105,14 @@ def load_library(build_if_missing=True):
         "splacu_v_eadd_fdb_sparse_emit": [vp, vp, vp, vp],
         "splacu_v_eadd_dense": [i32, i32, u32, vp, vp, vp, vp],
         "splacu_v_reduce_dense": [i32, i32, u32, vp, u32, vp, pu32, vp],
+        "splacu_mxv_masked_ops": [vp, i32, pop, pop, pop, vp, vp, vp, u32, i32, vp],
+        "splacu_vxm_masked_begin_ops": [vp, i32, pop, pop, pop, u32, vp, vp, vp, vp, pu32, vp],
+        "splacu_v_assign_masked_dense_ops": [i32, pop, pop, u32, vp, vp, u32, vp],
+        "splacu_v_assign_masked_sparse_ops": [i32, pop, pop, vp, u32, vp, vp, u32, vp],
+        "splacu_v_eadd_dense_op": [i32, pop, u32, vp, vp, vp, vp],
+        "splacu_v_eadd_fdb_dense_op": [i32, pop, u32, vp, vp, vp, u32, vp],
+        "splacu_v_eadd_fdb_sparse_begin_op": [i32, pop, vp, u32, vp, vp, vp, pu32, vp],
+        "splacu_jit_compile": [i32, pop, pop, pop, C.POINTER(C.c_size_t)], "splacu_jit_compile_count": [C.POINTER(C.c_uint64)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -205,6 +234,11 @@ class Backend:
             assert mask.numel() == M.n_rows and dtype_code(mask) == code
         if out is None:
             out = self.empty(M.n_rows, like=v)
+        if _user(op_mult, op_add, op_select):
+            om, oa, osel = make_op(op_mult, BIN), make_op(op_add, BIN), make_op(op_select, SEL)
+            self._check(self.lib.splacu_mxv_masked_ops(M.handle, code, C.byref(om), C.byref(oa), C.byref(osel), _ptr(v), _ptr(mask),
+                                                       _ptr(out), scalar_bits(code, init), int(bool(early_exit)), self.stream_ptr))
+            return out
         self._check(self.lib.splacu_mxv_masked(M.handle, code, BIN[op_mult], BIN[op_add], SEL[op_select], _ptr(v), _ptr(mask),
                                                _ptr(out), scalar_bits(code, init), int(bool(early_exit)), self.stream_ptr))
         return out
@@ -217,8 +251,13 @@ class Backend:
         assert vx.numel() == nv and (nv == 0 or dtype_code(vx) == code) and vi.dtype == torch.int32
         if mask is not None:
             assert mask.numel() == M.n_cols and dtype_code(mask) == code
-        self._check(self.lib.splacu_vxm_masked_begin(M.handle, code, BIN[op_mult], BIN[op_add], SEL[op_select], nv, _ptr(vi), _ptr(vx),
-                                                     _ptr(mask), self.ws, C.byref(self._nr), self.stream_ptr))
+        if _user(op_mult, op_add, op_select):
+            om, oa, osel = make_op(op_mult, BIN), make_op(op_add, BIN), make_op(op_select, SEL)
+            self._check(self.lib.splacu_vxm_masked_begin_ops(M.handle, code, C.byref(om), C.byref(oa), C.byref(osel), nv, _ptr(vi), _ptr(vx),
+                                                             _ptr(mask), self.ws, C.byref(self._nr), self.stream_ptr))
+        else:
+            self._check(self.lib.splacu_vxm_masked_begin(M.handle, code, BIN[op_mult], BIN[op_add], SEL[op_select], nv, _ptr(vi), _ptr(vx),
+                                                         _ptr(mask), self.ws, C.byref(self._nr), self.stream_ptr))
         nr = self._nr.value
         if out is not None:
             ri, rx = out[0][:nr], out[1][:nr]
@@ -228,6 +267,15 @@ class Backend:
                 rx = torch.empty(nr, dtype=M.Ax.dtype, device=self.device)
         self._check(self.lib.splacu_vxm_masked_emit(self.ws, _ptr(ri), _ptr(rx), self.stream_ptr))
         return ri, rx
+
+    def vxm_info(self):
+        """{"struct_only": bool}: did the last vxm_masked take the structure-only path (see include/splacu.h)"""
+        f = C.c_int(0)
+        self._check(self.lib.splacu_workspace_info(self.ws, C.byref(f)))
+        return {"struct_only": bool(f.value)}
+
+    def reset_workspace(self):
+        self._check(self.lib.splacu_workspace_reset(self.ws, self.stream_ptr))
 
     # ---- format glue ----
     def coo_to_dense(self, n, fill, vi, vx, out=None):
@@ -258,6 +306,14 @@ class Backend:
         """dense mask: exec_v_assign_masked(r, mask, value, op_assign, op_select); mask may be (mi, mx) sparse."""
         code = dtype_code(r)
         vb = scalar_bits(code, value)
+        if _user(op_assign, op_select):
+            oa, osel = make_op(op_assign, BIN), make_op(op_select, SEL)
+            if isinstance(mask, tuple):
+                mi, mx = mask
+                self._check(self.lib.splacu_v_assign_masked_sparse_ops(code, C.byref(oa), C.byref(osel), _ptr(r), mi.numel(), _ptr(mi), _ptr(mx), vb, self.stream_ptr))
+            else:
+                self._check(self.lib.splacu_v_assign_masked_dense_ops(code, C.byref(oa), C.byref(osel), r.numel(), _ptr(r), _ptr(mask), vb, self.stream_ptr))
+            return r
         if isinstance(mask, tuple):
             mi, mx = mask
             self._check(self.lib.splacu_v_assign_masked_sparse(code, BIN[op_assign], SEL[op_select], _ptr(r), mi.numel(), _ptr(mi), _ptr(mx),
@@ -292,13 +348,22 @@ class Backend:
         code = dtype_code(r)
         if fdb is None:
             fdb = self.empty(r.numel(), like=r)
+        if _user(op):
+            o = make_op(op, BIN)
+            self._check(self.lib.splacu_v_eadd_fdb_dense_op(code, C.byref(o), r.numel(), _ptr(r), _ptr(v), _ptr(fdb), scalar_bits(code, fdb_fill), self.stream_ptr))
+            return fdb
         self._check(self.lib.splacu_v_eadd_fdb_dense(code, BIN[op], r.numel(), _ptr(r), _ptr(v), _ptr(fdb), scalar_bits(code, fdb_fill), self.stream_ptr))
         return fdb
 
     def v_eadd_fdb_sparse(self, r, vi, vx, op):
         code = dtype_code(r)
-        self._check(self.lib.splacu_v_eadd_fdb_sparse_begin(code, BIN[op], _ptr(r), vi.numel(), _ptr(vi), _ptr(vx), self.ws, C.byref(self._nr),
-                                                            self.stream_ptr))
+        if _user(op):
+            o = make_op(op, BIN)
+            self._check(self.lib.splacu_v_eadd_fdb_sparse_begin_op(code, C.byref(o), _ptr(r), vi.numel(), _ptr(vi), _ptr(vx), self.ws, C.byref(self._nr),
+                                                                   self.stream_ptr))
+        else:
+            self._check(self.lib.splacu_v_eadd_fdb_sparse_begin(code, BIN[op], _ptr(r), vi.numel(), _ptr(vi), _ptr(vx), self.ws, C.byref(self._nr),
+                                                                self.stream_ptr))
         nf = self._nr.value
         with torch.cuda.stream(self.stream):
             fi = torch.empty(nf, dtype=torch.int32, device=self.device)
@@ -310,6 +375,10 @@ class Backend:
         code = dtype_code(u)
         if out is None:
             out = self.empty(u.numel(), like=u)
+        if _user(op):
+            o = make_op(op, BIN)
+            self._check(self.lib.splacu_v_eadd_dense_op(code, C.byref(o), u.numel(), _ptr(out), _ptr(u), _ptr(v), self.stream_ptr))
+            return out
         self._check(self.lib.splacu_v_eadd_dense(code, BIN[op], u.numel(), _ptr(out), _ptr(u), _ptr(v), self.stream_ptr))
         return out
 

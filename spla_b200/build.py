@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-diag-suppress", "186",
 ]
-SOURCES = ["runtime.cu", "vector_ops.cu", "mxv_pull.cu", "mxv_seg.cu", "vxm_push.cu"]
+SOURCES = ["runtime.cu", "vector_ops.cu", "mxv_pull.cu", "mxv_seg.cu", "vxm_push.cu", "jit.cu", "user_ops.cu"]
 
 
 def nvcc_path():
@@ -65,7 +65,7 @@ def build_splacu(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed:\n" + "\n".join(f"== {s} ==\n{o}" for s, o in failed))
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

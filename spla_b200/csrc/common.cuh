@@ -15,6 +15,7 @@ namespace splacu {
     int         cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     extern bool g_initialised;
     void        count_launch(int n = 1);
+    void        count_jit_compile();
 
 #define SPLACU_CUDA(expr)                                                          \
     do {                                                                           \
@@ -122,12 +123,15 @@ namespace splacu {
         CsrPhase  phase[kMaxHubPhases + 1];
         uint32_t* sel_count    = nullptr;// device counter: rows the mask of the current call selects (chooses the masked path on the device)
         uint32_t* sel_bits     = nullptr;// [n_rows / 32] bit i = select(mask[i]) of the current call: what the class passes read
+        // every stored value has the same bit pattern (adjacency matrices): lets the push product run structure-only (vxm_push.cu)
+        bool      ax_uniform   = false;
+        uint32_t  ax_value     = 0;
     };
 
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------
@@ -148,12 +152,17 @@ namespace splacu {
         // generic exact vxm path buffers
         uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr, *offsets = nullptr;
         size_t    cap_pairs = 0, cap_offsets = 0;
+        uint32_t* chunk_first = nullptr;// coarse index of the expanded frontier (vxm_push.cu)
+        size_t    cap_chunks  = 0;
         void*     sort_tmp = nullptr;
         size_t    cap_sort_tmp = 0;
         // small-front scratch (launch-latency paths): touched-column list of the push expand [kSmallList], compacted feedback
         // indices / values of the sparse eadd_fdb [2 * kSmallFront]
         uint32_t* small        = nullptr;
         bool      pend_small   = false;  // the pending emit reads the small-front scratch instead of the bitmap
+        bool      pend_const   = false;  // structure-only push: every result value is pend_value, acc[] was never touched
+        uint32_t  pend_value   = 0;
+        bool      last_struct  = false;  // the last vxm call took the structure-only path (introspection for tests / the bench)
         // pending emit state between *_begin and *_emit
         int       pending      = 0;      // 0 none, 1 vxm (acc/bitmap), 2 eadd_fdb sparse
         uint32_t  pend_n       = 0;      // length of the bitmap domain
@@ -169,6 +178,7 @@ namespace splacu {
     int ws_reserve_blocks(Workspace* ws, uint32_t n_blocks);
     int ws_reserve_selbits(Workspace* ws, uint32_t n);
     int ws_reserve_pairs(Workspace* ws, size_t n_pairs, size_t n_offsets);
+    int ws_reserve_chunks(Workspace* ws, size_t n_chunks);
 
     // ---- shared device-side building blocks (defined in vector_ops.cu) -----------------------
     // exclusive scan of n uint32 (in place allowed); total written to d_total (may be null)
@@ -177,7 +187,8 @@ namespace splacu {
     enum EmitMode {
         EMIT_ACC_RESET = 0,// (j, src[j]); afterwards src[j] = identity, bitmap word = 0     (vxm)
         EMIT_DENSE     = 1,// (j, src[j]); nothing reset                                      (dense -> coo)
-        EMIT_INDIRECT  = 2 // (vi[k], src[vi[k]]) for set bit k; bitmap word = 0              (eadd_fdb sparse)
+        EMIT_INDIRECT  = 2,// (vi[k], src[vi[k]]) for set bit k; bitmap word = 0              (eadd_fdb sparse)
+        EMIT_CONST     = 3 // (j, identity) -- one value for every entry; bitmap word = 0     (structure-only vxm)
     };
     // popcount the bitmap over [0, n) -> per-block sums scanned in ws->block_sums, total in ws->d_scalars[0]
     int bitmap_count(Workspace* ws, const uint32_t* d_bitmap, uint32_t n, cudaStream_t s);

@@ -423,6 +423,15 @@ namespace splacu {
         return 0;
     }
 
+    // every stored value equal to the first one? (adjacency matrices: the push product can then run structure-only)
+    __global__ void __launch_bounds__(kBlock) ax_uniform_kernel(const uint32_t* __restrict__ Ax, uint32_t nnz, uint32_t* __restrict__ differs) {
+        const uint32_t first  = Ax[0];
+        const uint32_t stride = gridDim.x * blockDim.x;
+        bool           d      = false;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) d |= Ax[k] != first;
+        if (__any_sync(0xffffffffu, d) && (threadIdx.x & 31u) == 0u) *differs = 1u;
+    }
+
     int csr_build_metadata(Csr* M, cudaStream_t s) {
         M->avg_row_nnz = M->n_rows ? (float) M->nnz / (float) M->n_rows : 0.f;
         M->vec_ok      = ((((uintptr_t) M->Aj) | ((uintptr_t) M->Ax)) & 15u) == 0;
@@ -434,6 +443,18 @@ namespace splacu {
         SPLACU_CUDA(cudaMalloc(&M->carry, (size_t) M->n_tiles * 2 * sizeof(uint32_t)));
         tile_rows_kernel<<<(M->n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->Ap, M->n_rows, M->tile, M->n_tiles, M->tile_rows);
         SPLACU_LAUNCH_CHECK();
+        {
+            // carry[] is per-call scratch: its first word doubles as the flag of this one-off check
+            uint32_t h[2] = {0u, 0u};
+            SPLACU_CUDA(cudaMemsetAsync(M->carry, 0, 4, s));
+            ax_uniform_kernel<<<grid_for(M->nnz, kBlock, 8), kBlock, 0, s>>>(M->Ax, M->nnz, M->carry);
+            SPLACU_LAUNCH_CHECK();
+            SPLACU_CUDA(cudaMemcpyAsync(&h[0], M->carry, 4, cudaMemcpyDeviceToHost, s));
+            SPLACU_CUDA(cudaMemcpyAsync(&h[1], M->Ax, 4, cudaMemcpyDeviceToHost, s));
+            SPLACU_CUDA(cudaStreamSynchronize(s));
+            M->ax_uniform = h[0] == 0u;
+            M->ax_value   = h[1];
+        }
         return build_hub(M, s);
     }
 

@@ -31,11 +31,14 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
+    static std::atomic<uint64_t> g_jit_compiles{0};
+    void count_jit_compile() { g_jit_compiles.fetch_add(1, std::memory_order_relaxed); }
+    uint64_t jit_compiles() { return g_jit_compiles.load(); }
 
     cudaStream_t resolve_stream(void* stream) { return stream ? (cudaStream_t) stream : g_stream; }
     int          sm_count() { return g_sm_count; }
@@ -100,9 +103,22 @@ namespace splacu {
             cudaFree(ws->offsets);
             ws->offsets = nullptr;
             size_t cap  = n_offsets + n_offsets / 4 + 1024;
-            SPLACU_CUDA(cudaMalloc(&ws->offsets, cap * 4));
+            SPLACU_CUDA(cudaMalloc(&ws->offsets, cap * 2 * 4));// [0, cap): frontier offsets, [cap, 2 cap): row starts Ap[vi[t]]
             ws->cap_offsets = cap;
         }
+        return 0;
+    }
+
+    int ws_reserve_chunks(Workspace* ws, size_t n_chunks) {
+        if (n_chunks <= ws->cap_chunks && ws->chunk_first) return 0;
+        if (ws->chunk_first) {
+            SPLACU_CUDA(cudaDeviceSynchronize());
+            cudaFree(ws->chunk_first);
+            ws->chunk_first = nullptr;
+        }
+        const size_t cap = n_chunks + n_chunks / 4 + 64;
+        SPLACU_CUDA(cudaMalloc(&ws->chunk_first, cap * 4));
+        ws->cap_chunks = cap;
         return 0;
     }
 
@@ -349,12 +365,29 @@ int splacu_workspace_create(splacu_workspace* out) {
     return SPLACU_OK;
 }
 
+int splacu_workspace_reset(splacu_workspace handle, void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_REQUIRE(handle, "null workspace");
+    Workspace* ws = reinterpret_cast<Workspace*>(handle);
+    ws->pending    = 0;
+    ws->pend_small = ws->pend_const = false;
+    ws->acc_clean  = false;// the accumulator is re-filled by the next push
+    if (ws->bitmap) SPLACU_CUDA(cudaMemsetAsync(ws->bitmap, 0, ((size_t) ws->cap_n + 31) / 32 * 4 + 4, resolve_stream(stream)));
+    return SPLACU_OK;
+}
+
+int splacu_workspace_info(splacu_workspace handle, int* struct_only) {
+    SPLACU_REQUIRE(handle, "null workspace");
+    if (struct_only) *struct_only = reinterpret_cast<Workspace*>(handle)->last_struct ? 1 : 0;
+    return SPLACU_OK;
+}
+
 int splacu_workspace_destroy(splacu_workspace handle) {
     if (!handle) return SPLACU_OK;
     Workspace* ws = reinterpret_cast<Workspace*>(handle);
     cudaFree(ws->acc); cudaFree(ws->bitmap); cudaFree(ws->sel_bits); cudaFree(ws->block_sums); cudaFree(ws->d_scalars); cudaFree(ws->small);
     cudaFreeHost(ws->h_scalars);
-    cudaFree(ws->keys_a); cudaFree(ws->keys_b); cudaFree(ws->vals_a); cudaFree(ws->vals_b); cudaFree(ws->offsets);
+    cudaFree(ws->keys_a); cudaFree(ws->keys_b); cudaFree(ws->vals_a); cudaFree(ws->vals_b); cudaFree(ws->offsets); cudaFree(ws->chunk_first);
     cudaFree(ws->sort_tmp);
     cudaGetLastError();
     delete ws;

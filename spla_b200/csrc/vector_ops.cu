@@ -170,6 +170,9 @@ namespace splacu {
                     const uint32_t i = vi[k];
                     ri[pos]          = i;
                     rx[pos]          = src[i];
+                } else if (MODE == EMIT_CONST) {
+                    ri[pos] = k;
+                    rx[pos] = identity;
                 } else {
                     ri[pos] = k;
                     rx[pos] = src[k];
@@ -207,6 +210,8 @@ namespace splacu {
             bitmap_emit_kernel<EMIT_ACC_RESET><<<nb, kBlock, 0, s>>>(d_bitmap, n_words, tail_mask, ws->block_sums, d_src, d_vi, identity, d_ri, d_rx);
         else if (mode == EMIT_DENSE)
             bitmap_emit_kernel<EMIT_DENSE><<<nb, kBlock, 0, s>>>(d_bitmap, n_words, tail_mask, ws->block_sums, d_src, d_vi, identity, d_ri, d_rx);
+        else if (mode == EMIT_CONST)
+            bitmap_emit_kernel<EMIT_CONST><<<nb, kBlock, 0, s>>>(d_bitmap, n_words, tail_mask, ws->block_sums, d_src, d_vi, identity, d_ri, d_rx);
         else
             bitmap_emit_kernel<EMIT_INDIRECT><<<nb, kBlock, 0, s>>>(d_bitmap, n_words, tail_mask, ws->block_sums, d_src, d_vi, identity, d_ri, d_rx);
         SPLACU_LAUNCH_CHECK();

@@ -15,6 +15,7 @@
 // expand (column, product) pairs at their deterministic frontier-order positions, stable radix sort by column,
 // strict left-to-right fold per column.
 #include "common.cuh"
+#include "jit.cuh"
 #include "ops.cuh"
 
 #include <cub/block/block_radix_sort.cuh>
@@ -26,19 +27,29 @@ namespace splacu {
     static constexpr int kBlock = 256;
     static constexpr int kEpt   = 8;// edge slots per thread per chunk
 
+    // deg[t] = length of row vi[t]; optionally also rowstart[t] = Ap[vi[t]] (so that the expand reads it sequentially instead of
+    // chasing vi -> Ap) and *differs |= (vx[t] != vx[0]) (bit patterns): the structure-only push needs one frontier value
     __global__ void __launch_bounds__(kBlock) vxm_degrees_kernel(uint32_t nv, const uint32_t* __restrict__ vi, const uint32_t* __restrict__ Ap,
-                                                                 uint32_t* __restrict__ deg) {
+                                                                 uint32_t* __restrict__ deg, uint32_t* __restrict__ rowstart,
+                                                                 const uint32_t* __restrict__ vx, uint32_t* __restrict__ differs) {
         const uint32_t stride = gridDim.x * blockDim.x;
+        const uint32_t x0     = vx ? vx[0] : 0u;
+        bool           d      = false;
         for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nv; t += stride) {
             const uint32_t i = vi[t];
-            deg[t]           = Ap[i + 1] - Ap[i];
+            const uint32_t a = Ap[i];
+            deg[t]           = Ap[i + 1] - a;
+            if (rowstart) rowstart[t] = a;
+            if (vx) d |= vx[t] != x0;
         }
+        if (vx && __any_sync(__activemask(), d) && d) *differs = 1u;
     }
 
     // Small fronts (nv <= kSmallFront) are launch-latency bound: ONE CTA gathers the degrees, scans them in shared memory and
     // clears the touched-column counter of the expand (instead of degree kernel + 3 scan launches).
     __global__ void __launch_bounds__(1024) vxm_offsets_small_kernel(uint32_t nv, const uint32_t* __restrict__ vi, const uint32_t* __restrict__ Ap,
-                                                                     uint32_t* __restrict__ off /*[nv + 1]*/, uint32_t* __restrict__ counter) {
+                                                                     uint32_t* __restrict__ off /*[nv + 1]*/, uint32_t* __restrict__ rowstart,
+                                                                     uint32_t* __restrict__ counter) {
         using BlockScan = cub::BlockScan<uint32_t, 1024>;
         __shared__ typename BlockScan::TempStorage tmp;
         constexpr int  kItems = kSmallFront / 1024;
@@ -50,7 +61,9 @@ namespace splacu {
             uint32_t       x = 0;
             if (t < nv) {
                 const uint32_t i = vi[t];
-                x                = Ap[i + 1] - Ap[i];
+                const uint32_t a = Ap[i];
+                x                = Ap[i + 1] - a;
+                rowstart[t]      = a;
             }
             d[k] = x;
         }
@@ -104,57 +117,180 @@ namespace splacu {
         return lo;
     }
 
+    // last t in [lo, hi) with off[t] <= e, given off[lo] <= e
+    __device__ __forceinline__ uint32_t find_entry_in(const uint32_t* __restrict__ off, uint32_t lo, uint32_t hi, uint32_t e) {
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (off[mid] <= e) lo = mid;
+            else hi = mid;
+        }
+        return lo;
+    }
+    // coarse index of the expanded frontier: first[c] = frontier entry that owns edge slot c * (kBlock * kEpt), first[n_chunks] = nv - 1.
+    // A thread of the expand then searches only between the entries of its chunk's borders -- a handful of offsets that all
+    // threads of the CTA share (L1 hits) -- instead of walking a 20-level binary search whose lower levels miss (ncu round 2: the
+    // searches were ~0.6 of the 2.3 L2 sectors per edge of the structure-only expand).
+    __global__ void __launch_bounds__(kBlock) vxm_chunk_index_kernel(const uint32_t* __restrict__ off, uint32_t nv, uint32_t* __restrict__ first) {
+        const uint32_t total    = off[nv];
+        const uint32_t chunk    = kBlock * kEpt;
+        const uint32_t n_chunks = (total + chunk - 1) / chunk;
+        const uint32_t stride   = gridDim.x * blockDim.x;
+        for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c <= n_chunks; c += stride)
+            first[c] = c < n_chunks ? find_entry(off, nv, c * chunk) : nv - 1u;
+    }
+
     // MODE 0: atomic accumulate into acc + bitmap (fast path). MODE 1: write (key, product) pairs (exact path).
-    // Every thread walks kEpt consecutive edge slots of the expanded frontier: no CTA barrier, 64 fully independent warps per
-    // SM hide the random-access latency. (Measured alternative, dropped: a CTA-tiled variant that stages the frontier entries of
-    // 2048 slots in shared memory and assigns slots round-robin for coalesced Aj loads was 2-3x SLOWER on the 400 M-edge level
-    // of an RMAT-24 BFS -- its barriers serialise the three dependent random accesses of a tile.)
+    // Every thread owns kEpt consecutive edge slots of the expanded frontier: no CTA barrier, 64 fully independent warps per SM.
+    // The slots are handled in PHASES, each a batch of kEpt independent loads: (1) walk the frontier entries, load the column ids
+    // and values (8 consecutive words per thread: one or two sectors when the loads are in flight together -- issued one edge at
+    // a time, with the random accesses of the previous edge in between, every one of them was its own L2 request, ncu round 2:
+    // 5.9 L2 sectors per edge), (2) the selection bits / mask values, (3) the accumulator words, (4) the atomics.
+    // rowstart[t] = Ap[vi[t]] comes from the degree kernel, so the walk reads three sequential arrays and never chases vi -> Ap.
+    // (Measured alternative, dropped: a CTA-tiled variant that stages the frontier entries of 2048 slots in shared memory and
+    // assigns slots round-robin for coalesced Aj loads was 2-3x SLOWER on the 400 M-edge level of an RMAT-24 BFS -- its barriers
+    // serialise the dependent random accesses of a tile.)
     template<typename T, typename S, int MODE>
-    __global__ void __launch_bounds__(kBlock) vxm_expand_kernel(S sr, Select sel, const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj,
-                                                                    const T* __restrict__ Ax, uint32_t nv, const uint32_t* __restrict__ vi,
+    __global__ void __launch_bounds__(kBlock) vxm_expand_kernel(S sr, Select sel, const uint32_t* __restrict__ Aj, const T* __restrict__ Ax, uint32_t nv,
                                                                     const T* __restrict__ vx, const T* __restrict__ mask,
                                                                     const uint32_t* __restrict__ sel_bits, const uint32_t* __restrict__ off /*[nv+1]*/,
+                                                                    const uint32_t* __restrict__ rowstart, const uint32_t* __restrict__ first,
                                                                     T* __restrict__ acc, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ keys,
                                                                     T* __restrict__ vals, uint32_t invalid_key, uint32_t identity_bits,
-                                                                    uint32_t* __restrict__ counter, uint32_t* __restrict__ list) {
+                                                                    uint32_t* __restrict__ counter, uint32_t* __restrict__ list,
+                                                                    const uint32_t* __restrict__ run_if /*null: always; else only when *run_if != 0*/) {
+        if (run_if && *run_if == 0u) return;// the structure-only kernel took this call
         const uint32_t total = off[nv];
         const uint32_t chunk = kBlock * kEpt;
         for (uint64_t base = (uint64_t) blockIdx.x * chunk; base < total; base += (uint64_t) gridDim.x * chunk) {
             if (base + threadIdx.x * kEpt >= total) continue;
-            uint32_t e = (uint32_t) base + threadIdx.x * kEpt;
-            const uint32_t e_end = min(total, e + kEpt);
-            uint32_t       t     = find_entry(off, nv, e);
+            const uint32_t e0    = (uint32_t) base + threadIdx.x * kEpt;
+            const uint32_t n_e   = min(total - e0, (uint32_t) kEpt);
+            const uint32_t c     = (uint32_t) (base / chunk);
+            uint32_t       t     = first ? find_entry_in(off, first[c], first[c + 1] + 1u, e0) : find_entry(off, nv, e0);
             uint32_t       t_end = off[t + 1];
-            uint32_t       row0  = Ap[vi[t]] - off[t];// k = row0 + e
+            uint32_t       row0  = rowstart[t] - off[t];// k = row0 + e
             T              x     = vx[t];
-            for (; e < e_end; ++e) {
-                while (e >= t_end) {// next frontier entry (skips entries with empty rows)
-                    ++t;
-                    t_end = off[t + 1];
-                    row0  = Ap[vi[t]] - off[t];
-                    x     = vx[t];
+            uint32_t       j[kEpt];
+            T              p[kEpt];
+            // (1) column ids and products
+#pragma unroll
+            for (int q = 0; q < kEpt; ++q) {
+                j[q] = 0u;
+                p[q] = T(0);
+                if ((uint32_t) q < n_e) {
+                    while (e0 + q >= t_end) {// next frontier entry (skips entries with empty rows)
+                        ++t;
+                        t_end = off[t + 1];
+                        row0  = rowstart[t] - off[t];
+                        x     = vx[t];
+                    }
+                    const uint32_t k = row0 + e0 + q;
+                    j[q]             = Aj[k];
+                    p[q]             = sr.mult(x, Ax[k]);
                 }
-                const uint32_t k = row0 + e;
-                const uint32_t j = Aj[k];
-                bool           take;
-                if (sel_bits) take = ((sel_bits[j >> 5] >> (j & 31u)) & 1u) != 0u;
-                else take = sel.reads_mask ? sel.test(mask[j]) : (sel.classes != 0u);
-                if (MODE == 0) {
-                    if (take) {
-                        const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&acc[j]);
-                        atomic_combine<T>(sr.add_op(), &acc[j], sr.mult(x, Ax[k]), from_bits<T>(cur));
-                        if (cur == identity_bits) {
-                            const uint32_t bit = 1u << (j & 31u);
-                            const uint32_t old = atomicOr(&bitmap[j >> 5], bit);
-                            if (counter && !(old & bit)) {// first touch of column j: count it, remember it while the list has room
-                                const uint32_t pos = atomicAdd(counter, 1u);
-                                if (pos < kSmallList) list[pos] = j;
-                            }
+            }
+            // (2) select(mask[j])
+            bool take[kEpt];
+            if (sel_bits) {
+                uint32_t w[kEpt];
+#pragma unroll
+                for (int q = 0; q < kEpt; ++q) w[q] = sel_bits[j[q] >> 5];
+#pragma unroll
+                for (int q = 0; q < kEpt; ++q) take[q] = (uint32_t) q < n_e && ((w[q] >> (j[q] & 31u)) & 1u) != 0u;
+            } else if (sel.reads_mask) {
+                T m[kEpt];
+#pragma unroll
+                for (int q = 0; q < kEpt; ++q) m[q] = mask[j[q]];
+#pragma unroll
+                for (int q = 0; q < kEpt; ++q) take[q] = (uint32_t) q < n_e && sel.test(m[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < kEpt; ++q) take[q] = (uint32_t) q < n_e && sel.classes != 0u;
+            }
+            if (MODE == 0) {
+                // (3) current accumulator words (possibly stale: they only serve to skip atomics that cannot change the value)
+                uint32_t cur[kEpt];
+#pragma unroll
+                for (int q = 0; q < kEpt; ++q) cur[q] = take[q] ? *reinterpret_cast<volatile uint32_t*>(&acc[j[q]]) : 0u;
+                // (4) fold
+#pragma unroll
+                for (int q = 0; q < kEpt; ++q) {
+                    if (!take[q]) continue;
+                    atomic_combine<T>(sr.add_op(), &acc[j[q]], p[q], from_bits<T>(cur[q]));
+                    if (cur[q] == identity_bits) {
+                        const uint32_t bit = 1u << (j[q] & 31u);
+                        const uint32_t old = atomicOr(&bitmap[j[q] >> 5], bit);
+                        if (counter && !(old & bit)) {// first touch of column j: count it, remember it while the list has room
+                            const uint32_t pos = atomicAdd(counter, 1u);
+                            if (pos < kSmallList) list[pos] = j[q];
                         }
                     }
-                } else {
-                    keys[e] = take ? j : invalid_key;
-                    vals[e] = take ? sr.mult(x, Ax[k]) : T(0);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < kEpt; ++q)
+                    if ((uint32_t) q < n_e) {
+                        keys[e0 + q] = take[q] ? j[q] : invalid_key;
+                        vals[e0 + q] = take[q] ? p[q] : T(0);
+                    }
+            }
+        }
+    }
+
+    // Structure-only push. When every product mult(x, a) is provably ONE value p (uniform frontier values x uniform matrix values,
+    // or a mult that ignores the varying side) and the add is idempotent on it (add(p, p) == p: MIN, MAX, BOR, BAND, and LOR / LAND
+    // over 0/1 products), the result is (j, p) for every column j reached through a selected edge -- the accumulator, Ax and vx are
+    // never read. `cand` starts as the select(mask) bitmap; an edge costs ONE L2 request (its word of cand, read through L2 so that
+    // a cleared bit is seen by every SM) instead of two (selection bit + accumulator word); the first edge to reach j clears its bit
+    // (atomicAnd) and, if it really was the first, records it in the touched bitmap the ordered emit reads. This is what a BFS level
+    // is (reference src/algorithm.cpp:97-99: BAND / BOR over a frontier of ones and an adjacency matrix of ones).
+    // `differs` != 0 (the frontier values are not uniform after all): the general kernel runs instead, this one returns at once.
+    __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+        uint32_t r;
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(p));
+        return r;
+    }
+    template<typename T, typename S>
+    __global__ void __launch_bounds__(kBlock) vxm_expand_struct_kernel(S sr, const uint32_t* __restrict__ Aj, uint32_t nv, const T* __restrict__ vx,
+                                                                           uint32_t ax_value, const uint32_t* __restrict__ off /*[nv+1]*/,
+                                                                           const uint32_t* __restrict__ rowstart, const uint32_t* __restrict__ first,
+                                                                           uint32_t* __restrict__ cand,
+                                                                           uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ differs,
+                                                                           uint32_t* __restrict__ value_out) {
+        if (differs && *differs) return;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *value_out = to_bits(sr.mult(vx[0], from_bits<T>(ax_value)));
+        const uint32_t total = off[nv];
+        const uint32_t chunk = kBlock * kEpt;
+        for (uint64_t base = (uint64_t) blockIdx.x * chunk; base < total; base += (uint64_t) gridDim.x * chunk) {
+            if (base + threadIdx.x * kEpt >= total) continue;
+            uint32_t       e     = (uint32_t) base + threadIdx.x * kEpt;
+            const uint32_t e_end = min(total, e + kEpt);
+            const uint32_t c     = (uint32_t) (base / chunk);
+            uint32_t       t     = first ? find_entry_in(off, first[c], first[c + 1] + 1u, e) : find_entry(off, nv, e);
+            uint32_t       t_end = off[t + 1];
+            uint32_t       row0  = rowstart[t] - off[t];// k = row0 + e
+            uint32_t       j[kEpt];
+            uint32_t       w[kEpt];
+#pragma unroll
+            for (int q = 0; q < kEpt; ++q) {
+                j[q] = 0xffffffffu;
+                if (e + q < e_end) {
+                    while (e + q >= t_end) {// next frontier entry (skips entries with empty rows)
+                        ++t;
+                        t_end = off[t + 1];
+                        row0  = rowstart[t] - off[t];
+                    }
+                    j[q] = Aj[row0 + e + q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kEpt; ++q) w[q] = j[q] != 0xffffffffu ? ld_cg_u32(cand + (j[q] >> 5)) : 0u;// all requests in flight together
+#pragma unroll
+            for (int q = 0; q < kEpt; ++q) {
+                const uint32_t bit = 1u << (j[q] & 31u);
+                if (w[q] & bit) {
+                    const uint32_t old = atomicAnd(&cand[j[q] >> 5], ~bit);
+                    if (old & bit) atomicOr(&bitmap[j[q] >> 5], bit);
                 }
             }
         }
@@ -230,15 +366,34 @@ namespace splacu {
         const bool fast  = fast_path_ok(op_mult, op_add);
         const bool small = fast && nv <= kSmallFront && get_option(OPT_SMALL_FRONT);
         uint32_t*  counter = small ? ws->d_scalars : nullptr;// the result count of a small front comes from the expand itself
+        // structure-only candidate: big frontier, idempotent add, products that cannot vary (decided here except for the
+        // uniformity of the frontier values, which the degree kernel checks on the device)
+        const bool idem      = op_add == SPLACU_MIN || op_add == SPLACU_MAX || op_add == SPLACU_BOR || op_add == SPLACU_BAND || op_add == SPLACU_LOR || op_add == SPLACU_LAND;
+        const bool ax_free   = op_mult == SPLACU_FIRST || op_mult == SPLACU_BONE; // vxm: mult(v, a)
+        const bool vx_free   = op_mult == SPLACU_SECOND || op_mult == SPLACU_BONE;
+        const bool strct     = fast && !small && idem && get_option(OPT_VXM_STRUCT) && (uint64_t) nv * 64 >= n && (M->ax_uniform || ax_free);
+        uint32_t*  differs   = strct ? ws->d_scalars + 2 : nullptr;
+        uint32_t*  rowstart  = ws->offsets + ws->cap_offsets;
+        ws->last_struct      = false;
         if (small) {
-            vxm_offsets_small_kernel<<<1, 1024, 0, s>>>(nv, d_vi, M->Ap, ws->offsets, counter);
+            vxm_offsets_small_kernel<<<1, 1024, 0, s>>>(nv, d_vi, M->Ap, ws->offsets, rowstart, counter);
             SPLACU_LAUNCH_CHECK();
         } else {
-            vxm_degrees_kernel<<<grid_for(nv, kBlock, 8), kBlock, 0, s>>>(nv, d_vi, M->Ap, ws->offsets);
+            if (strct) SPLACU_CUDA(cudaMemsetAsync(differs, 0, 8, s));// [2] differs, [3] the product
+            vxm_degrees_kernel<<<grid_for(nv, kBlock, 8), kBlock, 0, s>>>(nv, d_vi, M->Ap, ws->offsets, rowstart,
+                                                                         strct && !vx_free ? reinterpret_cast<const uint32_t*>(d_vx) : nullptr, differs);
             SPLACU_LAUNCH_CHECK();
             if ((rc = scan_exclusive_u32(ws, ws->offsets, ws->offsets, nv, ws->offsets + nv, s))) return rc;
         }
 
+        // coarse index of the expanded frontier (one entry per 2048 edge slots; sized for the whole matrix)
+        const uint32_t* chunk_first = nullptr;// small fronts are launch bound: they keep the full search
+        if (!small) {
+            if ((rc = ws_reserve_chunks(ws, (size_t) M->nnz / (kBlock * kEpt) + 2))) return rc;
+            vxm_chunk_index_kernel<<<grid_for((size_t) M->nnz / (kBlock * kEpt) + 2, kBlock, 8), kBlock, 0, s>>>(ws->offsets, nv, ws->chunk_first);
+            SPLACU_LAUNCH_CHECK();
+            chunk_first = ws->chunk_first;
+        }
         const T    identity = fast ? add_identity<T>(op_add) : from_bits<T>(ws->acc_identity);
         T*         acc      = reinterpret_cast<T*>(ws->acc);
         const int  grid     = sm_count() * 8;
@@ -250,17 +405,27 @@ namespace splacu {
                 ws->acc_clean    = true;
             }
             const uint32_t* sel_bits = nullptr;
-            if (sel.reads_mask && get_option(OPT_VXM_SELBITS) && (uint64_t) nv * 64 >= n) {
+            if (strct || (sel.reads_mask && get_option(OPT_VXM_SELBITS) && (uint64_t) nv * 64 >= n)) {
                 // (nv * 64 >= n: a frontier this large expands to at least ~n edges on the graphs this path sees)
                 if ((rc = ws_reserve_selbits(ws, n))) return rc;
-                select_bits_kernel<T><<<grid_for(n, kBlock, 8), kBlock, 0, s>>>(sel, d_mask, n, ws->sel_bits);
-                SPLACU_LAUNCH_CHECK();
-                sel_bits = ws->sel_bits;
+                if (sel.reads_mask) {
+                    select_bits_kernel<T><<<grid_for(n, kBlock, 8), kBlock, 0, s>>>(sel, d_mask, n, ws->sel_bits);
+                    SPLACU_LAUNCH_CHECK();
+                    sel_bits = ws->sel_bits;
+                } else {// ALWAYS, structure-only: every column is a candidate
+                    SPLACU_CUDA(cudaMemsetAsync(ws->sel_bits, 0xff, ((size_t) n + 31) / 32 * 4, s));
+                }
             }
             rc = dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
                 using S = decltype(sr);
-                vxm_expand_kernel<T, S, 0><<<grid, kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vi, d_vx, d_mask,
-                                                                   sel_bits, ws->offsets, acc, ws->bitmap, nullptr, nullptr, 0u, to_bits(identity), counter, ws->small);
+                if (strct) {
+                    vxm_expand_struct_kernel<T, S><<<grid, kBlock, 0, s>>>(sr, M->Aj, nv, d_vx, M->ax_value, ws->offsets, rowstart, chunk_first, ws->sel_bits,
+                                                                          ws->bitmap, differs, ws->d_scalars + 3);
+                    SPLACU_LAUNCH_CHECK();
+                }
+                vxm_expand_kernel<T, S, 0><<<grid, kBlock, 0, s>>>(sr, sel, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vx, d_mask,
+                                                                   sel_bits, ws->offsets, rowstart, chunk_first, acc, ws->bitmap, nullptr, nullptr, 0u, to_bits(identity), counter, ws->small,
+                                                                   strct ? differs : nullptr);
                 SPLACU_LAUNCH_CHECK();
                 return 0;
             });
@@ -276,9 +441,9 @@ namespace splacu {
                 sr.mul   = op_mult;
                 sr.ad    = op_add;
                 sr.ident = T(0);
-                vxm_expand_kernel<T, SemiringDynamic<T>, 1><<<grid, kBlock, 0, s>>>(sr, sel, M->Ap, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vi, d_vx,
-                                                                                   d_mask, nullptr, ws->offsets, nullptr, nullptr, ws->keys_a,
-                                                                                   reinterpret_cast<T*>(ws->vals_a), n, 0u, nullptr, nullptr);
+                vxm_expand_kernel<T, SemiringDynamic<T>, 1><<<grid, kBlock, 0, s>>>(sr, sel, M->Aj, reinterpret_cast<const T*>(M->Ax), nv, d_vx,
+                                                                                   d_mask, nullptr, ws->offsets, rowstart, chunk_first, nullptr, nullptr, ws->keys_a,
+                                                                                   reinterpret_cast<T*>(ws->vals_a), n, 0u, nullptr, nullptr, nullptr);
                 SPLACU_LAUNCH_CHECK();
                 int end_bit = 1;
                 while (end_bit < 32 && (n >> end_bit) != 0u) ++end_bit;// keys are in [0, n]
@@ -300,15 +465,78 @@ namespace splacu {
 
         // 3. count
         if (!small && (rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;
-        SPLACU_CUDA(cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, 4, cudaMemcpyDeviceToHost, s));
+        SPLACU_CUDA(cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, strct ? 16 : 4, cudaMemcpyDeviceToHost, s));
         SPLACU_CUDA(cudaStreamSynchronize(s));
         *h_nr             = ws->h_scalars[0];
+        ws->pend_const    = strct && ws->h_scalars[2] == 0u;// the frontier values were uniform: the structure-only kernel ran
+        ws->pend_value    = ws->h_scalars[3];
+        ws->last_struct   = ws->pend_const;
         ws->pend_small    = small && *h_nr <= kSmallList;
         if (small && !ws->pend_small && (rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;// block offsets for the bitmap emit
         ws->pending       = 1;
         ws->pend_n        = n;
         ws->pend_count    = *h_nr;
         ws->pend_identity = to_bits(identity);
+        return 0;
+    }
+
+    // User-defined ops (jit.cu): the exact ordered path with the user's mult / add / select inside -- offsets, (column, product) pairs
+    // at their frontier-order positions, stable radix sort by column, left-to-right fold per column (reference src/cpu/cpu_vxm.hpp:92-125).
+    int vxm_begin_jit(const Csr* M, const jit::Module* jm, uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask, Workspace* ws,
+                      uint32_t* h_nr, cudaStream_t s) {
+        uint32_t n = M->n_cols;
+        int      rc;
+        if ((rc = ws_reserve_vector(ws, n, s))) return rc;
+        if ((rc = ws_reserve_pairs(ws, 0, (size_t) nv + 1))) return rc;
+        uint32_t* rowstart = ws->offsets + ws->cap_offsets;
+        ws->last_struct    = false;
+        vxm_degrees_kernel<<<grid_for(nv, kBlock, 8), kBlock, 0, s>>>(nv, d_vi, M->Ap, ws->offsets, rowstart, nullptr, nullptr);
+        SPLACU_LAUNCH_CHECK();
+        if ((rc = scan_exclusive_u32(ws, ws->offsets, ws->offsets, nv, ws->offsets + nv, s))) return rc;
+        SPLACU_CUDA(cudaMemcpyAsync(ws->h_scalars + 1, ws->offsets + nv, 4, cudaMemcpyDeviceToHost, s));
+        SPLACU_CUDA(cudaStreamSynchronize(s));
+        uint32_t n_pairs = ws->h_scalars[1];
+        if (n_pairs) {
+            if ((rc = ws_reserve_pairs(ws, n_pairs, (size_t) nv + 1))) return rc;
+            rowstart              = ws->offsets + ws->cap_offsets;
+            const uint32_t* aj    = M->Aj;
+            const uint32_t* ax    = M->Ax;
+            const uint32_t* off   = ws->offsets;
+            uint32_t*       keys  = ws->keys_a;
+            uint32_t*       vals  = ws->vals_a;
+            uint32_t        inval = n;
+            void* a1[] = {&aj, &ax, &nv, &d_vx, &d_mask, &off, &rowstart, &keys, &vals, &inval};
+            if ((rc = jit::launch(jm, jit::K_VXM_PAIRS, n_pairs, a1, s))) return rc;
+            int end_bit = 1;
+            while (end_bit < 32 && (n >> end_bit) != 0u) ++end_bit;// keys are in [0, n]
+            size_t tmp_bytes = 0;
+            SPLACU_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ws->keys_a, ws->keys_b, ws->vals_a, ws->vals_b, (int) n_pairs, 0, end_bit, s));
+            if (tmp_bytes > ws->cap_sort_tmp) {
+                SPLACU_CUDA(cudaStreamSynchronize(s));
+                cudaFree(ws->sort_tmp);
+                ws->sort_tmp = nullptr;
+                SPLACU_CUDA(cudaMalloc(&ws->sort_tmp, tmp_bytes + tmp_bytes / 4));
+                ws->cap_sort_tmp = tmp_bytes + tmp_bytes / 4;
+            }
+            SPLACU_CUDA(cub::DeviceRadixSort::SortPairs(ws->sort_tmp, tmp_bytes, ws->keys_a, ws->keys_b, ws->vals_a, ws->vals_b, (int) n_pairs, 0, end_bit, s));
+            count_launch(8);
+            const uint32_t* skeys = ws->keys_b;
+            const uint32_t* svals = ws->vals_b;
+            uint32_t*       acc   = ws->acc;
+            uint32_t*       bm    = ws->bitmap;
+            void* a2[] = {&n_pairs, &skeys, &svals, &inval, &acc, &bm};
+            if ((rc = jit::launch(jm, jit::K_VXM_FOLD, n_pairs, a2, s))) return rc;
+        }
+        if ((rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;
+        SPLACU_CUDA(cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, 4, cudaMemcpyDeviceToHost, s));
+        SPLACU_CUDA(cudaStreamSynchronize(s));
+        *h_nr             = ws->h_scalars[0];
+        ws->pend_small    = false;
+        ws->pend_const    = false;
+        ws->pending       = 1;
+        ws->pend_n        = n;
+        ws->pend_count    = *h_nr;
+        ws->pend_identity = ws->acc_identity;// emit puts back what the accumulator was filled with
         return 0;
     }
 
@@ -382,6 +610,8 @@ int splacu_vxm_masked_emit(splacu_workspace wsh, uint32_t* d_ri, void* d_rx, voi
         SPLACU_LAUNCH_CHECK();
         return SPLACU_OK;
     }
+    if (ws->pend_const)// structure-only: one value for every touched column, the accumulator was never written
+        return bitmap_emit(ws, ws->bitmap, ws->pend_n, EMIT_CONST, nullptr, nullptr, ws->pend_value, d_ri, static_cast<uint32_t*>(d_rx), resolve_stream(stream));
     return bitmap_emit(ws, ws->bitmap, ws->pend_n, EMIT_ACC_RESET, ws->acc, nullptr, ws->pend_identity, d_ri, static_cast<uint32_t*>(d_rx),
                        resolve_stream(stream));
 }

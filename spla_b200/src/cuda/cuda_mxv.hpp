@@ -41,12 +41,8 @@ namespace spla {
             auto op_select   = t->op_select.template cast_safe<TOpSelect<T>>();
             auto init        = t->init.template cast_safe<TScalar<T>>();
 
-            const int id_mult = cuda_find_binop(op_multiply.get());
-            const int id_add  = cuda_find_binop(op_add.get());
-            const int id_sel  = cuda_find_selop(op_select.get());
-            SPLA_CUDA_REQUIRE_OP(id_mult, op_multiply);
-            SPLA_CUDA_REQUIRE_OP(id_add, op_add);
-            SPLA_CUDA_REQUIRE_OP(id_sel, op_select);
+            // built-ins by id (ahead-of-time specialised kernels), user-defined ops by source text (NVRTC, csrc/jit.cu)
+            CudaOpDesc d_mult(op_multiply.get()), d_add(op_add.get()), d_sel(op_select.get());
 
             r->validate_wd(FormatVector::AccDense);
             mask->validate_rw(FormatVector::AccDense);
@@ -60,9 +56,9 @@ namespace spla {
 
             const bool early_exit = t->get_desc_or_default()->get_early_exit();
 
-            SPLACU_CALL(splacu_mxv_masked(p_M->handle, cuda_dtype<T>(), id_mult, id_add, id_sel,
-                                          p_v->Ax.get(), p_mask->Ax.get(), p_r->Ax.get(),
-                                          cuda_bits(init->get_value()), early_exit ? 1 : 0, get_acc_cuda()->get_stream()));
+            SPLACU_CALL_OPS(splacu_mxv_masked_ops(p_M->handle, cuda_dtype<T>(), d_mult.get(), d_add.get(), d_sel.get(),
+                                                  p_v->Ax.get(), p_mask->Ax.get(), p_r->Ax.get(),
+                                                  cuda_bits(init->get_value()), early_exit ? 1 : 0, get_acc_cuda()->get_stream()));
             return Status::Ok;
         }
     };

@@ -37,10 +37,7 @@ namespace spla {
             auto op_assign = t->op_assign.template cast_safe<TOpBinary<T, T, T>>();
             auto op_select = t->op_select.template cast_safe<TOpSelect<T>>();
 
-            const int id_assign = cuda_find_binop(op_assign.get());
-            const int id_sel    = cuda_find_selop(op_select.get());
-            SPLA_CUDA_OP_OR_CPU(id_assign, ctx);
-            SPLA_CUDA_OP_OR_CPU(id_sel, ctx);
+            CudaOpDesc d_assign(op_assign.get()), d_sel(op_select.get());// user-defined ops: NVRTC (csrc/jit.cu)
 
             auto* acc = get_acc_cuda();
             // a dense mask is used as such; anything else (AccCoo, CpuCoo, CpuDok ...) goes through the sparse form
@@ -53,14 +50,14 @@ namespace spla {
             if (dense_mask) {
                 mask->validate_rw(FormatVector::AccDense);
                 const auto* p_mask = mask->template get<CudaDenseVec<T>>();
-                SPLACU_CALL(splacu_v_assign_masked_dense(cuda_dtype<T>(), id_assign, id_sel, r->get_n_rows(), p_r->Ax.get(), p_mask->Ax.get(),
-                                                         cuda_bits(value->get_value()), acc->get_stream()));
+                SPLACU_CALL_OPS(splacu_v_assign_masked_dense_ops(cuda_dtype<T>(), d_assign.get(), d_sel.get(), r->get_n_rows(), p_r->Ax.get(),
+                                                                 p_mask->Ax.get(), cuda_bits(value->get_value()), acc->get_stream()));
             } else {
                 mask->validate_rw(FormatVector::AccCoo);
                 const auto* p_mask = mask->template get<CudaCooVec<T>>();
-                SPLACU_CALL(splacu_v_assign_masked_sparse(cuda_dtype<T>(), id_assign, id_sel, p_r->Ax.get(), p_mask->values,
-                                                          static_cast<const uint32_t*>(p_mask->Ai.get()), p_mask->Ax.get(),
-                                                          cuda_bits(value->get_value()), acc->get_stream()));
+                SPLACU_CALL_OPS(splacu_v_assign_masked_sparse_ops(cuda_dtype<T>(), d_assign.get(), d_sel.get(), p_r->Ax.get(), p_mask->values,
+                                                                  static_cast<const uint32_t*>(p_mask->Ai.get()), p_mask->Ax.get(),
+                                                                  cuda_bits(value->get_value()), acc->get_stream()));
             }
             return Status::Ok;
         }
@@ -110,8 +107,7 @@ namespace spla {
             auto fdb = t->fdb.template cast_safe<TVector<T>>();
             auto op  = t->op.template cast_safe<TOpBinary<T, T, T>>();
 
-            const int id_op = cuda_find_binop(op.get());
-            SPLA_CUDA_OP_OR_CPU(id_op, ctx);
+            CudaOpDesc d_op(op.get());// user-defined op: NVRTC (csrc/jit.cu)
 
             auto*      acc     = get_acc_cuda();
             const bool dense_v = !v->is_valid(FormatVector::AccCoo) && !v->is_valid(FormatVector::CpuCoo) &&
@@ -125,17 +121,17 @@ namespace spla {
                 fdb->validate_wd(FormatVector::AccDense);
                 const auto* p_v   = v->template get<CudaDenseVec<T>>();
                 auto*       p_fdb = fdb->template get<CudaDenseVec<T>>();
-                SPLACU_CALL(splacu_v_eadd_fdb_dense(cuda_dtype<T>(), id_op, r->get_n_rows(), p_r->Ax.get(), p_v->Ax.get(), p_fdb->Ax.get(),
-                                                    cuda_bits(fdb->get_fill_value()), acc->get_stream()));
+                SPLACU_CALL_OPS(splacu_v_eadd_fdb_dense_op(cuda_dtype<T>(), d_op.get(), r->get_n_rows(), p_r->Ax.get(), p_v->Ax.get(), p_fdb->Ax.get(),
+                                                           cuda_bits(fdb->get_fill_value()), acc->get_stream()));
             } else {
                 v->validate_rw(FormatVector::AccCoo);
                 fdb->validate_wd(FormatVector::AccCoo);
                 const auto* p_v   = v->template get<CudaCooVec<T>>();
                 auto*       p_fdb = fdb->template get<CudaCooVec<T>>();
                 uint32_t    nf    = 0;
-                SPLACU_CALL(splacu_v_eadd_fdb_sparse_begin(cuda_dtype<T>(), id_op, p_r->Ax.get(), p_v->values,
-                                                           static_cast<const uint32_t*>(p_v->Ai.get()), p_v->Ax.get(), acc->get_workspace(), &nf,
-                                                           acc->get_stream()));
+                SPLACU_CALL_OPS(splacu_v_eadd_fdb_sparse_begin_op(cuda_dtype<T>(), d_op.get(), p_r->Ax.get(), p_v->values,
+                                                                  static_cast<const uint32_t*>(p_v->Ai.get()), p_v->Ax.get(), acc->get_workspace(), &nf,
+                                                                  acc->get_stream()));
                 cuda_coo_vec_resize(nf, *p_fdb);
                 SPLACU_CALL(splacu_v_eadd_fdb_sparse_emit(acc->get_workspace(), p_fdb->Ai.as_index(), p_fdb->Ax.get(), acc->get_stream()));
             }
@@ -159,8 +155,7 @@ namespace spla {
             auto v  = t->v.template cast_safe<TVector<T>>();
             auto op = t->op.template cast_safe<TOpBinary<T, T, T>>();
 
-            const int id_op = cuda_find_binop(op.get());
-            SPLA_CUDA_OP_OR_CPU(id_op, ctx);
+            CudaOpDesc d_op(op.get());// user-defined op: NVRTC (csrc/jit.cu)
 
             u->validate_rw(FormatVector::AccDense);
             v->validate_rw(FormatVector::AccDense);
@@ -170,8 +165,8 @@ namespace spla {
             const auto* p_v = v->template get<CudaDenseVec<T>>();
             auto*       p_r = r->template get<CudaDenseVec<T>>();
 
-            SPLACU_CALL(splacu_v_eadd_dense(cuda_dtype<T>(), id_op, r->get_n_rows(), p_r->Ax.get(), p_u->Ax.get(), p_v->Ax.get(),
-                                            get_acc_cuda()->get_stream()));
+            SPLACU_CALL_OPS(splacu_v_eadd_dense_op(cuda_dtype<T>(), d_op.get(), r->get_n_rows(), p_r->Ax.get(), p_u->Ax.get(), p_v->Ax.get(),
+                                                   get_acc_cuda()->get_stream()));
             return Status::Ok;
         }
     };

@@ -43,12 +43,8 @@ namespace spla {
             auto init        = t->init.template cast_safe<TScalar<T>>();// read, never used: reference src/cpu/cpu_vxm.hpp:72
             (void) init;
 
-            const int id_mult = cuda_find_binop(op_multiply.get());
-            const int id_add  = cuda_find_binop(op_add.get());
-            const int id_sel  = cuda_find_selop(op_select.get());
-            SPLA_CUDA_REQUIRE_OP(id_mult, op_multiply);
-            SPLA_CUDA_REQUIRE_OP(id_add, op_add);
-            SPLA_CUDA_REQUIRE_OP(id_sel, op_select);
+            // built-ins by id (ahead-of-time specialised kernels), user-defined ops by source text (NVRTC, csrc/jit.cu)
+            CudaOpDesc d_mult(op_multiply.get()), d_add(op_add.get()), d_sel(op_select.get());
 
             r->validate_wd(FormatVector::AccCoo);
             mask->validate_rw(FormatVector::AccDense);
@@ -64,9 +60,9 @@ namespace spla {
             splacu_workspace ws  = acc->get_workspace();
             uint32_t         nr  = 0;
 
-            SPLACU_CALL(splacu_vxm_masked_begin(p_M->handle, cuda_dtype<T>(), id_mult, id_add, id_sel,
-                                                p_v->values, static_cast<const uint32_t*>(p_v->Ai.get()), p_v->Ax.get(),
-                                                p_mask->Ax.get(), ws, &nr, acc->get_stream()));
+            SPLACU_CALL_OPS(splacu_vxm_masked_begin_ops(p_M->handle, cuda_dtype<T>(), d_mult.get(), d_add.get(), d_sel.get(),
+                                                        p_v->values, static_cast<const uint32_t*>(p_v->Ai.get()), p_v->Ax.get(),
+                                                        p_mask->Ax.get(), ws, &nr, acc->get_stream()));
             cuda_coo_vec_resize(nr, *p_r);
             SPLACU_CALL(splacu_vxm_masked_emit(ws, p_r->Ai.as_index(), p_r->Ax.get(), acc->get_stream()));
             return Status::Ok;

@@ -585,3 +585,72 @@ def test_pack_unpack_bits(backend, n):
             backend.unpack_bits(bits, n, 1, 0, out)
             backend.sync()
             assert np.array_equal(to_np(out, np_t), pred.astype(np_t)), (n, dtype, osel)
+
+
+@pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "BAND", "BOR", "EQZERO"), (INT, "LAND", "LOR", "EQZERO"), (UINT, "BAND", "BOR", "ALWAYS"),
+                                               (FLOAT, "PLUS", "MIN", "NQZERO"), (INT, "MULT", "MAX", "GEZERO"), (FLOAT, "LAND", "LOR", "EQZERO"),
+                                               (INT, "FIRST", "MIN", "EQZERO"), (INT, "SECOND", "BAND", "EQZERO"), (INT, "BONE", "LOR", "ALWAYS")])
+def test_push_structure_only_path(backend, oracle, dtype, om, oa, osel):
+    """Large frontiers whose products are provably ONE value under an idempotent add run structure-only (no Ax / vx / accumulator
+    reads): uniform frontier values x uniform matrix values, or a mult that ignores the varying side. The path must be taken when
+    it applies, must not be taken when the values vary (decided on the device), and both must match the oracle bit for bit --
+    including explicit zero products (note F: touched columns stay) and a second call on the same workspace."""
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, om, oa, "struct")).encode()))
+    n = 72000  # n / 8 frontier entries: above the small-front limit (8192), which keeps its own single-CTA path
+    Ap, Aj, Ax = cases.rand_csr(rng, dtype, n, n, 5, skew=False)
+    np_t = cases.NP[dtype]
+    for a_val, x_val in ((3, 5), (0, 2), (1, 1)):
+        Au = np.full(len(Aj), a_val, dtype=np_t)
+        M = make_csr(backend, n, n, Ap, Aj, Au)
+        vi = np.sort(rng.choice(n, size=n // 8, replace=False)).astype(np.uint32)  # nv * 64 >= n: a "large" frontier
+        mask = cases.rand_values(rng, dtype, n)
+        for uniform in (True, False, True):
+            vx = np.full(len(vi), x_val, dtype=np_t)
+            if not uniform:
+                vx[len(vx) // 2] = x_val + 1
+            wi, wx = oracle.vxm_masked(dtype, om, oa, osel, Ap, Aj, Au, n, vi, vx, mask)
+            gi, gx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(mask, backend), om, oa, osel)
+            backend.sync()
+            expect_struct = uniform or om in ("SECOND", "BONE")
+            assert backend.vxm_info()["struct_only"] == expect_struct, (om, oa, uniform)
+            assert np.array_equal(to_np(gi, np.uint32), wi), f"pattern {om}/{oa} uniform={uniform}"
+            assert_values(to_np(gx, np_t), wx, True, what=f"struct vxm {om}/{oa} a={a_val} x={x_val} uniform={uniform}")
+    # matrix values vary: never structure-only unless the mult ignores them
+    M = make_csr(backend, n, n, Ap, Aj, Ax)
+    vx = np.full(len(vi), 2, dtype=np_t)
+    wi, wx = oracle.vxm_masked(dtype, om, oa, osel, Ap, Aj, Ax, n, vi, vx, mask)
+    gi, gx = backend.vxm_masked(M, idx_dev(vi, backend), to_dev(vx, backend), to_dev(mask, backend), om, oa, osel)
+    backend.sync()
+    assert backend.vxm_info()["struct_only"] == (om in ("FIRST", "BONE"))
+    assert np.array_equal(to_np(gi, np.uint32), wi)
+    assert_values(to_np(gx, np_t), wx, True, what=f"struct vxm {om}/{oa} varying matrix")
+    # a sum is not idempotent: never structure-only
+    Au = np.full(len(Aj), 1, dtype=np_t)
+    M = make_csr(backend, n, n, Ap, Aj, Au)
+    backend.vxm_masked(M, idx_dev(vi, backend), to_dev(np.full(len(vi), 1, dtype=np_t), backend), to_dev(mask, backend), "MULT", "PLUS", osel)
+    backend.sync()
+    assert not backend.vxm_info()["struct_only"]
+
+
+def test_workspace_reset_after_abandoned_begin(backend, oracle):
+    """A begin() without its emit() (an exception in the caller) leaves the workspace pending; splacu_workspace_reset makes it usable again."""
+    import ctypes as C
+
+    rng = np.random.default_rng(8)
+    n = 3000
+    Ap, Aj, Ax = cases.rand_csr(rng, INT, n, n, 6)
+    M = make_csr(backend, n, n, Ap, Aj, Ax)
+    vi, vx = cases.rand_frontier(rng, INT, n, 200)
+    mask = cases.rand_values(rng, INT, n)
+    d_vi, d_vx, d_m = idx_dev(vi, backend), to_dev(vx, backend), to_dev(mask, backend)
+    nr = C.c_uint32(0)
+    from spla_b200.backend import BIN, SEL, _ptr
+
+    args = (M.handle, INT, BIN["MULT"], BIN["PLUS"], SEL["EQZERO"], len(vi), _ptr(d_vi), _ptr(d_vx), _ptr(d_m), backend.ws, C.byref(nr), backend.stream_ptr)
+    assert backend.lib.splacu_vxm_masked_begin(*args) == 0
+    assert backend.lib.splacu_vxm_masked_begin(*args) != 0  # pending emit: refused
+    backend.reset_workspace()
+    wi, wx = oracle.vxm_masked(INT, "MULT", "PLUS", "EQZERO", Ap, Aj, Ax, n, vi, vx, mask)
+    gi, gx = backend.vxm_masked(M, d_vi, d_vx, d_m, "MULT", "PLUS", "EQZERO")
+    backend.sync()
+    assert np.array_equal(to_np(gi, np.uint32), wi) and np.array_equal(to_np(gx, np.int32), wx)
