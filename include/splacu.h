@@ -78,6 +78,13 @@ SPLACU_API int         splacu_launch_count(uint64_t* count); /* kernels launched
 SPLACU_API int         splacu_set_option(const char* name, int64_t value);
 SPLACU_API int         splacu_get_option(const char* name, int64_t* value);
 
+/* profiling hooks (the reference: TIME_PROFILE_SCOPE labels with host / device times, src/profiling/time_profiler.hpp:44-100, dumped by
+ * Library::time_profile_dump). Every entry point of this header opens an NVTX range "splacu/<entry>"; with profiling enabled it
+ * also brackets its work with a cudaEvent pair on the launching stream. dump: "label, calls, device_ms, host_ms" lines. */
+SPLACU_API int         splacu_profile_enable(int on);
+SPLACU_API int         splacu_profile_reset(void);
+SPLACU_API int         splacu_profile_dump(char* buffer, int length);
+
 /* device memory: replaces cl::Buffer creation / enqueueRead / enqueueWrite in
  * reference src/opencl/cl_format_dense_vec.hpp:43-87, cl_format_coo_vec.hpp:43-125, cl_format_csr.hpp:40-96 */
 SPLACU_API int splacu_malloc(void** d_ptr, size_t bytes);
@@ -158,6 +165,13 @@ SPLACU_API int splacu_vxm_masked_begin(splacu_csr M, int dtype, int op_mult, int
                                        uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
                                        splacu_workspace ws, uint32_t* h_nr, void* stream);
 SPLACU_API int splacu_vxm_masked_emit(splacu_workspace ws, uint32_t* d_ri, void* d_rx, void* stream);
+/* begin, split at its host synchronisation: _begin_async only ENQUEUES (offsets, expand, count, the 4-byte copy), _begin_finish waits
+ * for the stream and returns the count. Lets a caller that drives several devices enqueue on all of them before it waits on any
+ * (the multi-GPU push below does). Op pairs that take the exact ordered path still synchronise inside _begin_async (sort sizing). */
+SPLACU_API int splacu_vxm_masked_begin_async(splacu_csr M, int dtype, int op_mult, int op_add, int op_select,
+                                             uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
+                                             splacu_workspace ws, void* stream);
+SPLACU_API int splacu_vxm_masked_begin_finish(splacu_workspace ws, uint32_t* h_nr, void* stream);
 
 /* One-call form over caller-provided buffers of `capacity` entries (n_cols always suffices). */
 SPLACU_API int splacu_vxm_masked(splacu_csr M, int dtype, int op_mult, int op_add, int op_select,
@@ -209,6 +223,38 @@ SPLACU_API int splacu_v_eadd_dense(int dtype, int op, uint32_t n, void* d_r, con
  * and commutative (PLUS, MULT, MIN, MAX, LOR, LAND, BOR, BAND, BXOR); FLOAT PLUS/MULT differ by summation order. */
 SPLACU_API int splacu_v_reduce_dense(int dtype, int op, uint32_t n, const void* d_v, uint32_t init_bits,
                                      splacu_workspace ws, uint32_t* h_result_bits, void* stream);
+
+/* ---- multi-GPU, single box (net-new: the reference is single-device and only reserves the knob,
+ *      Accelerator::set_queues_count, reference src/core/accelerator.hpp:58-69) -----------------------------------------------
+ * A group is N shards, one per listed device (a device may be listed more than once: several shards then share it -- how the
+ * sharding logic is tested on one GPU). device_ids[0] must be the home device (splacu_init): the caller's vectors live there, so
+ * every other entry point of this header keeps working on them unchanged. One host thread drives all shards; the products only
+ * ENQUEUE (events order the caller's stream before and after the shards' streams), except for the result count of the push.
+ *   pull  M row-sharded into contiguous blocks of ~nnz / N entries; a product = v to every shard (ncclBroadcast over NVLink when the
+ *         shards sit on distinct devices and libnccl.so.2 is present, peer copies otherwise), mask / result windows by peer copies,
+ *         N local splacu_mxv_masked concurrently.
+ *   push  M column-sharded (windows nnz-balanced on the column histogram, slices built at the first push); every shard expands the
+ *         whole frontier against its slice under its mask window; the output is the concatenation of the shards' results.
+ * Results are those of the single-device entry points: bit-exact for integer / order-independent work; FLOAT sums may differ in
+ * summation order (the column classes are built per shard). Built-in ops only (user-defined ops: use the single-device handle). */
+typedef struct splacu_dist_t* splacu_dist;
+typedef struct splacu_dcsr_t* splacu_dcsr;
+SPLACU_API int splacu_dist_create(splacu_dist* group, int n_shards, const int* device_ids);
+SPLACU_API int splacu_dist_destroy(splacu_dist group);
+SPLACU_API int splacu_dist_info(splacu_dist group, int* n_shards, int* uses_nccl);
+/* d_Ap / d_Aj / d_Ax: the CSR on the home device (not owned; shard 0 works on them in place) */
+SPLACU_API int splacu_dcsr_create(splacu_dcsr* M, splacu_dist group, uint32_t n_rows, uint32_t n_cols, uint32_t nnz,
+                                  const uint32_t* d_Ap, const uint32_t* d_Aj, const void* d_Ax, void* stream);
+SPLACU_API int splacu_dcsr_destroy(splacu_dcsr M);
+/* row_bounds / col_bounds: n_shards + 1 entries each (either may be NULL; col_bounds are all zero before the first push) */
+SPLACU_API int splacu_dcsr_bounds(splacu_dcsr M, int* n_shards, uint32_t* row_bounds, uint32_t* col_bounds);
+/* same arguments and semantics as splacu_mxv_masked; d_v, d_mask, d_r on the home device */
+SPLACU_API int splacu_dist_mxv_masked(splacu_dcsr M, int dtype, int op_mult, int op_add, int op_select,
+                                      const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits, int early_exit, void* stream);
+/* same arguments and semantics as splacu_vxm_masked_begin / _emit (the scratch is the group's: one workspace per shard) */
+SPLACU_API int splacu_dist_vxm_masked_begin(splacu_dcsr M, int dtype, int op_mult, int op_add, int op_select,
+                                            uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask, uint32_t* h_nr, void* stream);
+SPLACU_API int splacu_dist_vxm_masked_emit(splacu_dcsr M, uint32_t* d_ri, void* d_rx, void* stream);
 
 /* ---- user-defined ops -----------------------------------------------------------------------------
  * The reference compiles the SOURCE TEXT of a user op, "(T a, T b) { ... }" (OpBinary::make_int/uint/float, OpSelect::make_*,

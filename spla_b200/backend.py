@@ -40,6 +40,10 @@ SYMBOLS = [
     "splacu_v_eadd_fdb_dense", "splacu_v_eadd_fdb_sparse_begin", "splacu_v_eadd_fdb_sparse_emit",
     "splacu_v_eadd_dense", "splacu_v_reduce_dense",
     "splacu_mxv_masked_ops", "splacu_vxm_masked_begin_ops", "splacu_v_assign_masked_dense_ops", "splacu_v_assign_masked_sparse_ops",
+    "splacu_profile_enable", "splacu_profile_reset", "splacu_profile_dump",
+    "splacu_vxm_masked_begin_async", "splacu_vxm_masked_begin_finish",
+    "splacu_dist_create", "splacu_dist_destroy", "splacu_dist_info", "splacu_dcsr_create", "splacu_dcsr_destroy", "splacu_dcsr_bounds",
+    "splacu_dist_mxv_masked", "splacu_dist_vxm_masked_begin", "splacu_dist_vxm_masked_emit",
     "splacu_v_eadd_dense_op", "splacu_v_eadd_fdb_dense_op", "splacu_v_eadd_fdb_sparse_begin_op", "splacu_jit_compile", "splacu_jit_compile_count",
 ]
 
@@ -112,6 +116,13 @@ def load_library(build_if_missing=True):
         "splacu_v_eadd_dense_op": [i32, pop, u32, vp, vp, vp, vp],
         "splacu_v_eadd_fdb_dense_op": [i32, pop, u32, vp, vp, vp, u32, vp],
         "splacu_v_eadd_fdb_sparse_begin_op": [i32, pop, vp, u32, vp, vp, vp, pu32, vp],
+        "splacu_profile_enable": [i32], "splacu_profile_reset": [], "splacu_profile_dump": [C.c_char_p, i32],
+        "splacu_vxm_masked_begin_async": [vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, vp], "splacu_vxm_masked_begin_finish": [vp, pu32, vp],
+        "splacu_dist_create": [C.POINTER(vp), i32, C.POINTER(C.c_int)], "splacu_dist_destroy": [vp], "splacu_dist_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "splacu_dcsr_create": [C.POINTER(vp), vp, u32, u32, u32, vp, vp, vp, vp], "splacu_dcsr_destroy": [vp],
+        "splacu_dcsr_bounds": [vp, C.POINTER(C.c_int), pu32, pu32],
+        "splacu_dist_mxv_masked": [vp, i32, i32, i32, i32, vp, vp, vp, u32, i32, vp],
+        "splacu_dist_vxm_masked_begin": [vp, i32, i32, i32, i32, u32, vp, vp, vp, pu32, vp], "splacu_dist_vxm_masked_emit": [vp, vp, vp, vp],
         "splacu_jit_compile": [i32, pop, pop, pop, C.POINTER(C.c_size_t)], "splacu_jit_compile_count": [C.POINTER(C.c_uint64)],
     }
     for name, args in sig.items():
@@ -165,6 +176,75 @@ class CsrMatrix:
         if getattr(self, "handle", None) is not None:
             try:
                 self.backend.lib.splacu_csr_destroy(self.handle)
+            except Exception:
+                pass
+            self.handle = None
+
+
+class DistGroup:
+    def __init__(self, backend, device_ids):
+        self.backend = backend
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        h = C.c_void_p()
+        backend._check(backend.lib.splacu_dist_create(C.byref(h), len(device_ids), ids))
+        self.handle, self.n = h, len(device_ids)
+        n, nc = C.c_int(0), C.c_int(0)
+        backend.lib.splacu_dist_info(h, C.byref(n), C.byref(nc))
+        self.uses_nccl = bool(nc.value)
+
+    def csr(self, M):
+        """shard a CsrMatrix of this backend over the group"""
+        return DistCsr(self, M)
+
+    def __del__(self):
+        if getattr(self, "handle", None) is not None:
+            try:
+                self.backend.lib.splacu_dist_destroy(self.handle)
+            except Exception:
+                pass
+            self.handle = None
+
+
+class DistCsr:
+    def __init__(self, group, M):
+        self.group, self.M, self.backend = group, M, group.backend
+        h = C.c_void_p()
+        be = self.backend
+        be._check(be.lib.splacu_dcsr_create(C.byref(h), group.handle, M.n_rows, M.n_cols, M.nnz, _ptr(M.Ap), _ptr(M.Aj), _ptr(M.Ax), be.stream_ptr))
+        self.handle = h
+        self._nr = C.c_uint32(0)
+
+    def bounds(self):
+        n = C.c_int(0)
+        rb, cb = (C.c_uint32 * 17)(), (C.c_uint32 * 17)()
+        self.backend._check(self.backend.lib.splacu_dcsr_bounds(self.handle, C.byref(n), rb, cb))
+        return [int(rb[p]) for p in range(n.value + 1)], [int(cb[p]) for p in range(n.value + 1)]
+
+    def mxv_masked(self, v, mask, op_mult, op_add, op_select, init, early_exit=False, out=None):
+        be, M = self.backend, self.M
+        code = M.dtype
+        if out is None:
+            out = be.empty(M.n_rows, like=v)
+        be._check(be.lib.splacu_dist_mxv_masked(self.handle, code, BIN[op_mult], BIN[op_add], SEL[op_select], _ptr(v), _ptr(mask), _ptr(out),
+                                                scalar_bits(code, init), int(bool(early_exit)), be.stream_ptr))
+        return out
+
+    def vxm_masked(self, vi, vx, mask, op_mult, op_add, op_select):
+        be, M = self.backend, self.M
+        code = M.dtype
+        be._check(be.lib.splacu_dist_vxm_masked_begin(self.handle, code, BIN[op_mult], BIN[op_add], SEL[op_select], vi.numel(), _ptr(vi), _ptr(vx),
+                                                      _ptr(mask), C.byref(self._nr), be.stream_ptr))
+        nr = self._nr.value
+        with torch.cuda.stream(be.stream):
+            ri = torch.empty(nr, dtype=torch.int32, device=be.device)
+            rx = torch.empty(nr, dtype=M.Ax.dtype, device=be.device)
+        be._check(be.lib.splacu_dist_vxm_masked_emit(self.handle, _ptr(ri), _ptr(rx), be.stream_ptr))
+        return ri, rx
+
+    def __del__(self):
+        if getattr(self, "handle", None) is not None:
+            try:
+                self.backend.lib.splacu_dcsr_destroy(self.handle)
             except Exception:
                 pass
             self.handle = None
@@ -268,6 +348,21 @@ class Backend:
         self._check(self.lib.splacu_vxm_masked_emit(self.ws, _ptr(ri), _ptr(rx), self.stream_ptr))
         return ri, rx
 
+    def profile(self, on=True):
+        """cudaEvent timing of every C-ABI entry point under its label (NVTX ranges are always emitted)"""
+        self._check(self.lib.splacu_profile_enable(int(bool(on))))
+
+    def profile_dump(self, reset=True):
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.splacu_profile_dump(buf, len(buf)))
+        if reset:
+            self.lib.splacu_profile_reset()
+        rows = {}
+        for ln in buf.value.decode().splitlines()[1:]:
+            label, calls, dev, host = [x.strip() for x in ln.split(",")]
+            rows[label] = {"calls": int(calls), "device_ms": float(dev), "host_ms": float(host)}
+        return rows
+
     def vxm_info(self):
         """{"struct_only": bool}: did the last vxm_masked take the structure-only path (see include/splacu.h)"""
         f = C.c_int(0)
@@ -276,6 +371,11 @@ class Backend:
 
     def reset_workspace(self):
         self._check(self.lib.splacu_workspace_reset(self.ws, self.stream_ptr))
+
+    # ---- multi-GPU behind the C ABI (include/splacu.h "multi-GPU, single box") ----
+    def dist_group(self, device_ids):
+        """N shards, one per listed device (ids may repeat: shards share a device); device_ids[0] must be this backend's device"""
+        return DistGroup(self, device_ids)
 
     # ---- format glue ----
     def coo_to_dense(self, n, fill, vi, vx, out=None):

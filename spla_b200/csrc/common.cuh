@@ -47,8 +47,11 @@ namespace splacu {
         if (_e != cudaSuccess) return ::splacu::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
     } while (0)
 
+    // stream == NULL selects the backend's own in-order stream of the CURRENT device (one per initialised device)
     cudaStream_t resolve_stream(void* stream);
     int          sm_count();
+    int          current_device();
+    int          ensure_device(int device);// create the backend stream of a further device (multi-GPU group, dist.cu)
 
     // grid sized as a multiple of the SM count for grid-stride kernels
     inline int grid_for(size_t work_items, int block, int ctas_per_sm) {
@@ -163,8 +166,11 @@ namespace splacu {
         bool      pend_const   = false;  // structure-only push: every result value is pend_value, acc[] was never touched
         uint32_t  pend_value   = 0;
         bool      last_struct  = false;  // the last vxm call took the structure-only path (introspection for tests / the bench)
+        // an enqueued push whose count has not been read yet (vxm_begin_typed -> vxm_finish)
+        bool      fin_strct = false, fin_small = false;
+        uint32_t  fin_n = 0, fin_identity = 0;
         // pending emit state between *_begin and *_emit
-        int       pending      = 0;      // 0 none, 1 vxm (acc/bitmap), 2 eadd_fdb sparse
+        int       pending      = 0;      // 0 none, 1 vxm (acc/bitmap), 2 eadd_fdb sparse, 3 dense_to_coo, 4 vxm enqueued (begin_async)
         uint32_t  pend_n       = 0;      // length of the bitmap domain
         uint32_t  pend_count   = 0;
         uint32_t  pend_identity = 0;

@@ -28,6 +28,7 @@
 //   mxv_seq_kernel      one thread per row, strict left-to-right fold: the exact path for non-associative adds
 //                       (MINUS, DIV, FIRST, SECOND, BONE, MINUS_POW2) without early_exit.
 #include "common.cuh"
+#include "profile.cuh"
 #include "ops.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -995,10 +996,11 @@ namespace splacu {
     static int launch_wtile(S sr, Select sel, const TileJob& job, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
         auto           kern = mxv_wtile_kernel<T, S, MASKED, MODE, WARPS>;
         const uint32_t smem = (uint32_t) WARPS * kSliceWords * 4u + (MODE != MODE_PLAIN ? ((job.n_smem + 3u) & ~3u) * 4u : 0u);
-        static bool    attr_done = false;// per instantiation
-        if (!attr_done) {
+        static uint64_t attr_done = 0;// per instantiation, one bit per device: a function attribute belongs to the device it was set on
+        const int       dev_bit   = current_device() & 63;
+        if (!((attr_done >> dev_bit) & 1u)) {
             SPLACU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemLimit));
-            attr_done = true;
+            attr_done |= (uint64_t) 1 << dev_bit;
         }
         const uint32_t want = (job.n_tiles + WARPS - 1) / WARPS;
         const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
@@ -1020,25 +1022,16 @@ namespace splacu {
 
     // keep v resident in L2 while the CSR arrays stream through it (access-policy window on the launching stream)
     static int set_persisting_window(const void* base, size_t bytes, cudaStream_t s) {
-        static const void*  cur_base  = nullptr;
-        static size_t       cur_bytes = 0;
-        static cudaStream_t cur_s     = nullptr;
-        static size_t       max_win = 0, max_persist = 0;
-        static bool         probed = false;
-        if (!probed) {
-            probed = true;
-            int dev = 0, v1 = 0, v2 = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&v1, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-            cudaDeviceGetAttribute(&v2, cudaDevAttrMaxPersistingL2CacheSize, dev);
-            max_win     = (size_t) v1;
-            max_persist = (size_t) v2;
-            if (max_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, max_persist);
-            cudaGetLastError();
-        }
+        // (opt-in, off by default: measured no gain) -- nothing is cached across calls: the limits belong to the current device
+        int dev = 0, v1 = 0, v2 = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v1, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaDeviceGetAttribute(&v2, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        const size_t max_win = (size_t) v1, max_persist = (size_t) v2;
         if (!max_win || !max_persist) return 0;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, max_persist);
+        cudaGetLastError();
         if (bytes > max_win) bytes = max_win;
-        if (base == cur_base && bytes == cur_bytes && s == cur_s) return 0;
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
         attr.accessPolicyWindow.base_ptr  = const_cast<void*>(base);
@@ -1047,7 +1040,6 @@ namespace splacu {
         attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
         attr.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
         SPLACU_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
-        cur_base = base, cur_bytes = bytes, cur_s = s;
         return 0;
     }
 
@@ -1106,6 +1098,7 @@ using namespace splacu;
 extern "C" int splacu_mxv_masked(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select,
                                  const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits, int early_exit, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/mxv_masked", resolve_stream(stream));
     SPLACU_REQUIRE(handle, "null matrix handle");
     const Csr* M = reinterpret_cast<const Csr*>(handle);
     SPLACU_REQUIRE(op_valid_for(dtype, op_mult), "op_mult not defined for dtype");

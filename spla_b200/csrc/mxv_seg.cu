@@ -353,10 +353,11 @@ namespace splacu {
         constexpr int  kW   = IDX16 ? kSegWarps : kSegTailWarps;
         auto           kern = mxv_seg_kernel<T, S, MASKED, IDX16, kW>;
         const uint32_t smem = kW * 512u * 4u + (IDX16 ? ((ph.n_slots + 3u) & ~3u) * 4u : 0u);
-        static bool    attr_done = false;// per instantiation
-        if (!attr_done) {
+        static uint64_t attr_done = 0;// per instantiation, one bit per device: a function attribute belongs to the device it was set on
+        const int       dev_bit   = current_device() & 63;
+        if (!((attr_done >> dev_bit) & 1u)) {
             SPLACU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemMax));
-            attr_done = true;
+            attr_done |= (uint64_t) 1 << dev_bit;
         }
         if (smem > kSmemMax) {
             set_error("mxv: hub class of %u slots does not fit in shared memory", ph.n_slots);

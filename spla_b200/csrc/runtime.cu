@@ -2,6 +2,7 @@
 // device CSR handle and workspace. Replaces the OpenCL runtime of the reference
 // (src/opencl/cl_accelerator.cpp:84-201, cl_alloc_*.cpp, cl_counter.cpp) for the hot path.
 #include "common.cuh"
+#include "profile.cuh"
 
 #include <atomic>
 #include <cstdarg>
@@ -10,10 +11,14 @@
 
 namespace splacu {
 
+    // One backend stream per device. g_device is the HOME device (splacu_init): where the caller's vectors live and where every
+    // single-device entry point runs; a multi-GPU group (dist.cu) initialises further devices through ensure_device().
+    static constexpr int  kMaxDevices   = 64;
     bool                  g_initialised = false;
     static int            g_device      = -1;
     static int            g_sm_count    = 148;
-    static cudaStream_t   g_stream      = nullptr;
+    static cudaStream_t   g_streams[kMaxDevices] = {};
+#define g_stream g_streams[g_device >= 0 ? g_device : 0]
     static char           g_device_name[256] = "none";
     static std::atomic<uint64_t> g_launches{0};
     static thread_local char     g_error[1024] = "";
@@ -40,8 +45,27 @@ namespace splacu {
     void count_jit_compile() { g_jit_compiles.fetch_add(1, std::memory_order_relaxed); }
     uint64_t jit_compiles() { return g_jit_compiles.load(); }
 
-    cudaStream_t resolve_stream(void* stream) { return stream ? (cudaStream_t) stream : g_stream; }
-    int          sm_count() { return g_sm_count; }
+    int current_device() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return dev;
+    }
+    cudaStream_t resolve_stream(void* stream) {
+        if (stream) return (cudaStream_t) stream;
+        const int dev = current_device();
+        return (dev >= 0 && dev < kMaxDevices && g_streams[dev]) ? g_streams[dev] : g_stream;
+    }
+    int sm_count() { return g_sm_count; }
+    int ensure_device(int device) {
+        SPLACU_REQUIRE(device >= 0 && device < kMaxDevices, "device index out of range");
+        if (g_streams[device]) return 0;
+        const int prev = current_device();
+        SPLACU_CUDA(cudaSetDevice(device));
+        cudaError_t e = cudaStreamCreateWithFlags(&g_streams[device], cudaStreamNonBlocking);
+        cudaSetDevice(prev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+        return 0;
+    }
 
     int ws_reserve_vector(Workspace* ws, uint32_t n, cudaStream_t s) {
         if (n <= ws->cap_n && ws->acc) return 0;
@@ -148,12 +172,11 @@ int splacu_init(int device) {
     cudaDeviceProp prop;
     SPLACU_CUDA(cudaGetDeviceProperties(&prop, device));
     if (g_initialised && g_device == device) return SPLACU_OK;
-    if (g_stream) {
-        cudaStreamDestroy(g_stream);
-        g_stream = nullptr;
-    }
-    SPLACU_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-    g_device   = device;
+    // switching the home device: the stream of the old one stays alive (handles and workspaces created there keep working
+    // as long as their device is current when they are used); per-device state -- function attributes, JIT modules -- is keyed
+    // by device
+    g_device = device;
+    if (!g_stream) SPLACU_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     g_sm_count = prop.multiProcessorCount;
     snprintf(g_device_name, sizeof(g_device_name), "%s (sm_%d%d, %d SMs, %.0f GB)", prop.name, prop.major, prop.minor,
              prop.multiProcessorCount, (double) prop.totalGlobalMem / 1e9);
@@ -162,11 +185,16 @@ int splacu_init(int device) {
 }
 
 int splacu_finalize(void) {
-    if (g_stream) {
-        cudaStreamSynchronize(g_stream);
-        cudaStreamDestroy(g_stream);
-        g_stream = nullptr;
-    }
+    const int prev = current_device();
+    for (int d = 0; d < kMaxDevices; ++d)
+        if (g_streams[d]) {
+            cudaSetDevice(d);
+            cudaStreamSynchronize(g_streams[d]);
+            cudaStreamDestroy(g_streams[d]);
+            g_streams[d] = nullptr;
+        }
+    cudaSetDevice(prev);
+    cudaGetLastError();
     g_initialised = false;
     g_device      = -1;
     return SPLACU_OK;
@@ -195,7 +223,7 @@ int splacu_sm_count(int* count) {
     return SPLACU_OK;
 }
 
-void* splacu_default_stream(void) { return (void*) g_stream; }
+void* splacu_default_stream(void) { return g_device >= 0 ? (void*) g_stream : nullptr; }
 
 int splacu_sync(void* stream) {
     SPLACU_CHECK_INIT();
@@ -310,6 +338,7 @@ int splacu_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream
 int splacu_csr_create(splacu_csr* out, uint32_t n_rows, uint32_t n_cols, uint32_t nnz,
                       const uint32_t* d_Ap, const uint32_t* d_Aj, const void* d_Ax, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/csr_create", resolve_stream(stream));
     SPLACU_REQUIRE(out, "null handle pointer");
     SPLACU_REQUIRE(d_Ap, "null Ap");
     SPLACU_REQUIRE(nnz == 0 || (d_Aj && d_Ax), "null Aj/Ax");

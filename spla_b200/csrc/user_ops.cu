@@ -3,6 +3,7 @@
 // Replaces the per-kernel JIT of the reference's OpenCL backend (src/opencl/cl_program_builder.cpp:65-120) for the hot path and
 // its neighbour tasks.
 #include "common.cuh"
+#include "profile.cuh"
 #include "jit.cuh"
 #include "ops.cuh"
 
@@ -40,6 +41,7 @@ int splacu_jit_compile_count(uint64_t* count) {
 int splacu_mxv_masked_ops(splacu_csr handle, int dtype, const splacu_op* m, const splacu_op* a, const splacu_op* sl, const void* d_v,
                           const void* d_mask, void* d_r, uint32_t init_bits, int early_exit, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/mxv_masked_ops", resolve_stream(stream));
     SPLACU_REQUIRE(handle && m && a && sl, "null handle / op");
     if (!jit::is_user(m) && !jit::is_user(a) && !jit::is_user(sl))
         return splacu_mxv_masked(handle, dtype, m->id, a->id, sl->id, d_v, d_mask, d_r, init_bits, early_exit, stream);
@@ -61,6 +63,7 @@ int splacu_mxv_masked_ops(splacu_csr handle, int dtype, const splacu_op* m, cons
 int splacu_vxm_masked_begin_ops(splacu_csr handle, int dtype, const splacu_op* m, const splacu_op* a, const splacu_op* sl, uint32_t nv,
                                 const uint32_t* d_vi, const void* d_vx, const void* d_mask, splacu_workspace wsh, uint32_t* h_nr, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/vxm_masked_begin_ops", resolve_stream(stream));
     SPLACU_REQUIRE(handle && wsh && h_nr && m && a && sl, "null handle / op");
     if (!jit::is_user(m) && !jit::is_user(a) && !jit::is_user(sl))
         return splacu_vxm_masked_begin(handle, dtype, m->id, a->id, sl->id, nv, d_vi, d_vx, d_mask, wsh, h_nr, stream);

@@ -6,6 +6,7 @@
 // All kernels are HBM-bound streaming passes: 128-bit accesses where alignment allows, grid sized in
 // multiples of the SM count, grid-stride loops.
 #include "common.cuh"
+#include "profile.cuh"
 #include "ops.cuh"
 
 #include <cub/block/block_scan.cuh>
@@ -452,6 +453,7 @@ int splacu_fill(void* d_dst, uint32_t value_bits, size_t n, void* stream) {
 
 int splacu_coo_to_dense(uint32_t n, uint32_t fill_bits, uint32_t nv, const uint32_t* d_vi, const void* d_vx, void* d_dense, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/coo_to_dense", resolve_stream(stream));
     SPLACU_REQUIRE(d_dense || n == 0, "null dense pointer");
     int rc = splacu_fill(d_dense, fill_bits, n, stream);
     if (rc) return rc;
@@ -472,6 +474,7 @@ static int read_scalar0(Workspace* ws, uint32_t* h_out, cudaStream_t s) {
 
 int splacu_dense_to_coo_count(int dtype, uint32_t n, uint32_t fill_bits, const void* d_dense, splacu_workspace handle, uint32_t* h_nr, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/dense_to_coo_count", resolve_stream(stream));
     SPLACU_REQUIRE(handle && h_nr, "null pointer");
     Workspace*   ws = reinterpret_cast<Workspace*>(handle);
     cudaStream_t s  = resolve_stream(stream);
@@ -503,6 +506,7 @@ int splacu_dense_to_coo_emit(int dtype, uint32_t n, uint32_t fill_bits, const vo
     (void) dtype;
     (void) fill_bits;
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/dense_to_coo_emit", resolve_stream(stream));
     SPLACU_REQUIRE(handle, "null workspace");
     Workspace*   ws = reinterpret_cast<Workspace*>(handle);
     cudaStream_t s  = resolve_stream(stream);
@@ -522,6 +526,7 @@ int splacu_dense_to_coo_emit(int dtype, uint32_t n, uint32_t fill_bits, const vo
 
 int splacu_v_assign_masked_dense(int dtype, int op_assign, int op_select, uint32_t n, void* d_r, const void* d_mask, uint32_t value_bits, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/v_assign_masked", resolve_stream(stream));
     SPLACU_REQUIRE(op_valid_for(dtype, op_assign), "op_assign not defined for dtype");
     SPLACU_REQUIRE(op_select >= 0 && op_select < SPLACU_SELOP_COUNT, "unknown op_select");
     if (n == 0) return SPLACU_OK;
@@ -539,6 +544,7 @@ int splacu_v_assign_masked_dense(int dtype, int op_assign, int op_select, uint32
 int splacu_v_assign_masked_sparse(int dtype, int op_assign, int op_select, void* d_r, uint32_t nm, const uint32_t* d_mi, const void* d_mx,
                                   uint32_t value_bits, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/v_assign_masked", resolve_stream(stream));
     SPLACU_REQUIRE(op_valid_for(dtype, op_assign), "op_assign not defined for dtype");
     SPLACU_REQUIRE(op_select >= 0 && op_select < SPLACU_SELOP_COUNT, "unknown op_select");
     if (nm == 0) return SPLACU_OK;
@@ -555,6 +561,7 @@ int splacu_v_assign_masked_sparse(int dtype, int op_assign, int op_select, void*
 
 int splacu_v_count_mf_dense(int dtype, uint32_t n, const void* d_v, uint32_t fill_bits, splacu_workspace handle, uint32_t* h_count, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/v_count_mf", resolve_stream(stream));
     SPLACU_REQUIRE(handle && h_count, "null pointer");
     Workspace*   ws = reinterpret_cast<Workspace*>(handle);
     cudaStream_t s  = resolve_stream(stream);
@@ -574,6 +581,7 @@ int splacu_v_count_mf_dense(int dtype, uint32_t n, const void* d_v, uint32_t fil
 
 int splacu_v_eadd_fdb_dense(int dtype, int op, uint32_t n, void* d_r, const void* d_v, void* d_fdb, uint32_t fdb_fill_bits, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/v_eadd_fdb", resolve_stream(stream));
     SPLACU_REQUIRE(op_valid_for(dtype, op), "op not defined for dtype");
     if (n == 0) return SPLACU_OK;
     SPLACU_REQUIRE(d_r && d_v && d_fdb, "null pointer");
@@ -589,6 +597,7 @@ int splacu_v_eadd_fdb_dense(int dtype, int op, uint32_t n, void* d_r, const void
 int splacu_v_eadd_fdb_sparse_begin(int dtype, int op, void* d_r, uint32_t nv, const uint32_t* d_vi, const void* d_vx,
                                    splacu_workspace handle, uint32_t* h_nf, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/v_eadd_fdb", resolve_stream(stream));
     SPLACU_REQUIRE(op_valid_for(dtype, op), "op not defined for dtype");
     SPLACU_REQUIRE(handle && h_nf, "null pointer");
     Workspace*   ws = reinterpret_cast<Workspace*>(handle);
@@ -638,6 +647,7 @@ int splacu_v_eadd_fdb_sparse_begin(int dtype, int op, void* d_r, uint32_t nv, co
 
 int splacu_v_eadd_fdb_sparse_emit(splacu_workspace handle, uint32_t* d_fi, void* d_fx, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/v_eadd_fdb_emit", resolve_stream(stream));
     SPLACU_REQUIRE(handle, "null workspace");
     Workspace*   ws = reinterpret_cast<Workspace*>(handle);
     cudaStream_t s  = resolve_stream(stream);
@@ -659,6 +669,7 @@ int splacu_v_eadd_fdb_sparse_emit(splacu_workspace handle, uint32_t* d_fi, void*
 
 int splacu_v_eadd_dense(int dtype, int op, uint32_t n, void* d_r, const void* d_u, const void* d_v, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/v_eadd", resolve_stream(stream));
     SPLACU_REQUIRE(op_valid_for(dtype, op), "op not defined for dtype");
     if (n == 0) return SPLACU_OK;
     SPLACU_REQUIRE(d_r && d_u && d_v, "null pointer");
@@ -673,6 +684,7 @@ int splacu_v_eadd_dense(int dtype, int op, uint32_t n, void* d_r, const void* d_
 
 int splacu_v_reduce_dense(int dtype, int op, uint32_t n, const void* d_v, uint32_t init_bits, splacu_workspace handle, uint32_t* h_result_bits, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/v_reduce", resolve_stream(stream));
     SPLACU_REQUIRE(op_valid_for(dtype, op), "op not defined for dtype");
     SPLACU_REQUIRE(is_assoc_commutative(op), "v_reduce needs an associative and commutative op on the device");
     SPLACU_REQUIRE(handle && h_result_bits, "null pointer");

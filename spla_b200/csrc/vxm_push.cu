@@ -15,6 +15,7 @@
 // expand (column, product) pairs at their deterministic frontier-order positions, stable radix sort by column,
 // strict left-to-right fold per column.
 #include "common.cuh"
+#include "profile.cuh"
 #include "jit.cuh"
 #include "ops.cuh"
 
@@ -354,9 +355,11 @@ namespace splacu {
         }
     }
 
+    int vxm_finish(Workspace* ws, uint32_t* h_nr, cudaStream_t s);
+
     template<typename T>
     static int vxm_begin_typed(const Csr* M, int op_mult, int op_add, const Select& sel, uint32_t nv, const uint32_t* d_vi, const T* d_vx,
-                               const T* d_mask, Workspace* ws, uint32_t* h_nr, cudaStream_t s) {
+                               const T* d_mask, Workspace* ws, uint32_t* h_nr, cudaStream_t s, bool defer_finish) {
         const uint32_t n = M->n_cols;
         int            rc;
         if ((rc = ws_reserve_vector(ws, n, s))) return rc;
@@ -463,20 +466,32 @@ namespace splacu {
             }
         }
 
-        // 3. count
+        // 3. count: enqueued here, read by vxm_finish (the one host synchronisation of the call)
         if (!small && (rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;
         SPLACU_CUDA(cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, strct ? 16 : 4, cudaMemcpyDeviceToHost, s));
+        ws->fin_strct    = strct;
+        ws->fin_small    = small;
+        ws->fin_n        = n;
+        ws->fin_identity = to_bits(identity);
+        ws->pending      = 4;// enqueued, not yet finished
+        if (defer_finish) return 0;
+        return vxm_finish(ws, h_nr, s);
+    }
+
+    int vxm_finish(Workspace* ws, uint32_t* h_nr, cudaStream_t s) {
+        int rc;
         SPLACU_CUDA(cudaStreamSynchronize(s));
+        const bool strct = ws->fin_strct, small = ws->fin_small;
         *h_nr             = ws->h_scalars[0];
         ws->pend_const    = strct && ws->h_scalars[2] == 0u;// the frontier values were uniform: the structure-only kernel ran
         ws->pend_value    = ws->h_scalars[3];
         ws->last_struct   = ws->pend_const;
         ws->pend_small    = small && *h_nr <= kSmallList;
-        if (small && !ws->pend_small && (rc = bitmap_count(ws, ws->bitmap, n, s))) return rc;// block offsets for the bitmap emit
+        if (small && !ws->pend_small && (rc = bitmap_count(ws, ws->bitmap, ws->fin_n, s))) return rc;// block offsets for the bitmap emit
         ws->pending       = 1;
-        ws->pend_n        = n;
+        ws->pend_n        = ws->fin_n;
         ws->pend_count    = *h_nr;
-        ws->pend_identity = to_bits(identity);
+        ws->pend_identity = ws->fin_identity;
         return 0;
     }
 
@@ -570,11 +585,11 @@ int splacu_v_unpack_bits(uint32_t n, const uint32_t* d_bits, uint32_t one_bits, 
     return SPLACU_OK;
 }
 
-int splacu_vxm_masked_begin(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select,
-                            uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
-                            splacu_workspace wsh, uint32_t* h_nr, void* stream) {
+static int vxm_begin_common(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select, uint32_t nv, const uint32_t* d_vi, const void* d_vx,
+                            const void* d_mask, splacu_workspace wsh, uint32_t* h_nr, void* stream, bool defer_finish) {
     SPLACU_CHECK_INIT();
-    SPLACU_REQUIRE(handle && wsh && h_nr, "null handle");
+    SPLACU_PROFILE("splacu/vxm_masked_begin", resolve_stream(stream));
+    SPLACU_REQUIRE(handle && wsh && (h_nr || defer_finish), "null handle");
     const Csr* M  = reinterpret_cast<const Csr*>(handle);
     Workspace* ws = reinterpret_cast<Workspace*>(wsh);
     SPLACU_REQUIRE(op_valid_for(dtype, op_mult), "op_mult not defined for dtype");
@@ -582,19 +597,43 @@ int splacu_vxm_masked_begin(splacu_csr handle, int dtype, int op_mult, int op_ad
     SPLACU_REQUIRE(op_select >= 0 && op_select < SPLACU_SELOP_COUNT, "unknown op_select");
     SPLACU_REQUIRE(ws->pending == 0, "workspace has a pending emit");
     const Select sel = make_select(op_select);
-    *h_nr            = 0;
+    if (h_nr) *h_nr = 0;
     if (nv == 0 || M->n_cols == 0 || M->nnz == 0 || sel.classes == 0u) return SPLACU_OK;// nothing can be touched
     SPLACU_REQUIRE(d_vi && d_vx, "null frontier pointers");
     SPLACU_REQUIRE(d_mask || !sel.reads_mask, "null mask pointer");
     cudaStream_t s = resolve_stream(stream);
     return dispatch_dtype(dtype, [&](auto tag) {
         using T = decltype(tag);
-        return vxm_begin_typed<T>(M, op_mult, op_add, sel, nv, d_vi, static_cast<const T*>(d_vx), static_cast<const T*>(d_mask), ws, h_nr, s);
+        return vxm_begin_typed<T>(M, op_mult, op_add, sel, nv, d_vi, static_cast<const T*>(d_vx), static_cast<const T*>(d_mask), ws, h_nr, s, defer_finish);
     });
+}
+
+int splacu_vxm_masked_begin(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select,
+                            uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
+                            splacu_workspace wsh, uint32_t* h_nr, void* stream) {
+    return vxm_begin_common(handle, dtype, op_mult, op_add, op_select, nv, d_vi, d_vx, d_mask, wsh, h_nr, stream, false);
+}
+
+int splacu_vxm_masked_begin_async(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select,
+                                  uint32_t nv, const uint32_t* d_vi, const void* d_vx, const void* d_mask,
+                                  splacu_workspace wsh, void* stream) {
+    return vxm_begin_common(handle, dtype, op_mult, op_add, op_select, nv, d_vi, d_vx, d_mask, wsh, nullptr, stream, true);
+}
+
+int splacu_vxm_masked_begin_finish(splacu_workspace wsh, uint32_t* h_nr, void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/vxm_masked_begin_finish", resolve_stream(stream));
+    SPLACU_REQUIRE(wsh && h_nr, "null pointer");
+    Workspace* ws = reinterpret_cast<Workspace*>(wsh);
+    *h_nr         = 0;
+    if (ws->pending == 0) return SPLACU_OK;// the async begin short-circuited on an empty product
+    SPLACU_REQUIRE(ws->pending == 4, "begin_finish without a matching begin_async");
+    return vxm_finish(ws, h_nr, resolve_stream(stream));
 }
 
 int splacu_vxm_masked_emit(splacu_workspace wsh, uint32_t* d_ri, void* d_rx, void* stream) {
     SPLACU_CHECK_INIT();
+    SPLACU_PROFILE("splacu/vxm_masked_emit", resolve_stream(stream));
     SPLACU_REQUIRE(wsh, "null workspace");
     Workspace* ws = reinterpret_cast<Workspace*>(wsh);
     if (ws->pending == 0) return SPLACU_OK;// begin() short-circuited on an empty product

@@ -38,7 +38,14 @@ namespace spla {
 
     /**
      * @class CudaAccelerator
-     * @brief Single-device CUDA acceleration backend
+     * @brief CUDA acceleration backend: one home device, optionally a group of devices for the two products
+     *
+     * The vectors of a program always live on the home device (set_device). With more than one device requested --
+     * Library::set_queues_count(n), the knob the reference reserves for parallel queues (src/core/accelerator.hpp:58-69,
+     * src/library.cpp:136-138), or the environment variable SPLA_CUDA_DEVICES=n read at init -- mxv_masked / vxm_masked run
+     * sharded over n devices of the box (splacu_dist_*: rows nnz-balanced for the pull, columns for the push, v broadcast
+     * over NVLink with NCCL); everything else is unchanged. SPLA_CUDA_SHARE_DEVICES=1 lets the shards wrap around the
+     * devices present (n shards on fewer GPUs: for testing).
      */
     class CudaAccelerator final : public Accelerator {
     public:
@@ -56,13 +63,19 @@ namespace spla {
         splacu_workspace get_workspace() { return m_workspace; }
         /** the backend's in-order stream (NULL selects it on the C-ABI side) */
         void* get_stream() { return nullptr; }
+        /** the device group of the sharded products, or nullptr when a single device is used */
+        splacu_dist get_group() { return m_group; }
 
     private:
         std::string      m_name        = "CUDA";
         std::string      m_description = "no device";
         std::string      m_suffix      = GPU_CUDA_SUFFIX;
         splacu_workspace m_workspace   = nullptr;
+        splacu_dist      m_group       = nullptr;
         int              m_device      = 0;
+        int              m_n_devices   = 1;
+
+        Status rebuild_group();
     };
 
     /** @return the active CUDA accelerator; throws when another (or no) accelerator is installed */

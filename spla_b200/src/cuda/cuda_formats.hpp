@@ -98,12 +98,24 @@ namespace spla {
     public:
         static constexpr FormatMatrix FORMAT = FormatMatrix::AccCsr;
         ~CudaCsr() override {
+            if (dhandle) splacu_dcsr_destroy(dhandle);
             if (handle) splacu_csr_destroy(handle);
         }
-        CudaBuffer Ap;
-        CudaBuffer Aj;
-        CudaBuffer Ax;
-        splacu_csr handle = nullptr;
+        CudaBuffer  Ap;
+        CudaBuffer  Aj;
+        CudaBuffer  Ax;
+        splacu_csr  handle  = nullptr;
+        splacu_dcsr dhandle = nullptr;// the matrix sharded over the accelerator's device group, built at the first product that uses it
+        uint        n_rows = 0, n_cols = 0;
+
+        /** the sharded handle when the accelerator drives several devices, else nullptr */
+        splacu_dcsr sharded() {
+            splacu_dist group = get_acc_cuda()->get_group();
+            if (!group) return nullptr;
+            if (!dhandle)
+                SPLACU_CALL(splacu_dcsr_create(&dhandle, group, n_rows, n_cols, this->values, Ap.as_index(), Aj.as_index(), Ax.get(), nullptr));
+            return dhandle;
+        }
     };
 
     // ---- dense vector ------------------------------------------------------------------------------------------------
@@ -174,10 +186,16 @@ namespace spla {
 
     template<typename T>
     void cuda_csr_init(uint n_rows, uint n_cols, uint n_values, const uint* Ap, const uint* Aj, const T* Ax, CudaCsr<T>& storage) {
+        if (storage.dhandle) {
+            splacu_dcsr_destroy(storage.dhandle);
+            storage.dhandle = nullptr;
+        }
         if (storage.handle) {
             splacu_csr_destroy(storage.handle);
             storage.handle = nullptr;
         }
+        storage.n_rows = n_rows;
+        storage.n_cols = n_cols;
         storage.Ap.reserve(std::size_t(n_rows) + 1);
         storage.Aj.reserve(n_values);
         storage.Ax.reserve(n_values);

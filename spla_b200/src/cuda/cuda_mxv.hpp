@@ -51,10 +51,20 @@ namespace spla {
 
             auto*       p_r    = r->template get<CudaDenseVec<T>>();
             const auto* p_mask = mask->template get<CudaDenseVec<T>>();
-            const auto* p_M    = M->template get<CudaCsr<T>>();
+            auto*       p_M    = M->template get<CudaCsr<T>>();
             const auto* p_v    = v->template get<CudaDenseVec<T>>();
 
             const bool early_exit = t->get_desc_or_default()->get_early_exit();
+
+            // several devices (CudaAccelerator::set_queues_count / SPLA_CUDA_DEVICES): rows sharded, v broadcast over NVLink
+            if (!d_mult.user_defined() && !d_add.user_defined() && !d_sel.user_defined()) {
+                if (splacu_dcsr sharded = p_M->sharded()) {
+                    SPLACU_CALL(splacu_dist_mxv_masked(sharded, cuda_dtype<T>(), d_mult.get()->id, d_add.get()->id, d_sel.get()->id,
+                                                       p_v->Ax.get(), p_mask->Ax.get(), p_r->Ax.get(), cuda_bits(init->get_value()),
+                                                       early_exit ? 1 : 0, get_acc_cuda()->get_stream()));
+                    return Status::Ok;
+                }
+            }
 
             SPLACU_CALL_OPS(splacu_mxv_masked_ops(p_M->handle, cuda_dtype<T>(), d_mult.get(), d_add.get(), d_sel.get(),
                                                   p_v->Ax.get(), p_mask->Ax.get(), p_r->Ax.get(),

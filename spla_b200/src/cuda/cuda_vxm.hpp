@@ -53,12 +53,24 @@ namespace spla {
 
             auto*       p_r    = r->template get<CudaCooVec<T>>();
             const auto* p_mask = mask->template get<CudaDenseVec<T>>();
-            const auto* p_M    = M->template get<CudaCsr<T>>();
+            auto*       p_M    = M->template get<CudaCsr<T>>();
             const auto* p_v    = v->template get<CudaCooVec<T>>();
 
             auto*            acc = get_acc_cuda();
             splacu_workspace ws  = acc->get_workspace();
             uint32_t         nr  = 0;
+
+            // several devices: columns sharded, every shard expands the whole frontier against its slice
+            if (!d_mult.user_defined() && !d_add.user_defined() && !d_sel.user_defined()) {
+                if (splacu_dcsr sharded = p_M->sharded()) {
+                    SPLACU_CALL(splacu_dist_vxm_masked_begin(sharded, cuda_dtype<T>(), d_mult.get()->id, d_add.get()->id, d_sel.get()->id, p_v->values,
+                                                             static_cast<const uint32_t*>(p_v->Ai.get()), p_v->Ax.get(), p_mask->Ax.get(), &nr,
+                                                             acc->get_stream()));
+                    cuda_coo_vec_resize(nr, *p_r);
+                    SPLACU_CALL(splacu_dist_vxm_masked_emit(sharded, p_r->Ai.as_index(), p_r->Ax.get(), acc->get_stream()));
+                    return Status::Ok;
+                }
+            }
 
             SPLACU_CALL_OPS(splacu_vxm_masked_begin_ops(p_M->handle, cuda_dtype<T>(), d_mult.get(), d_add.get(), d_sel.get(),
                                                         p_v->values, static_cast<const uint32_t*>(p_v->Ai.get()), p_v->Ax.get(),

@@ -64,3 +64,39 @@ def test_reference_gtests_on_cuda_backend(binary):
     rc, out = run(binary)
     assert rc == 0, out[-3000:]
     assert "[  PASSED  ]" in out and "FAILED" not in out, out[-3000:]
+
+
+def _gpu_count():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@needs_build
+@pytest.mark.parametrize("shards", ["2", "3"])
+def test_cuda_backend_sharded_matches_cpu_backend(shards):
+    """The same differential test with the two products SHARDED behind spla's public API (CudaAccelerator device group: rows
+    nnz-balanced for mxv, columns for vxm; SPLA_CUDA_DEVICES). On a single-GPU box the shards share the device
+    (SPLA_CUDA_SHARE_DEVICES); with several GPUs visible they sit on distinct devices and v travels by ncclBroadcast."""
+    env = {"SPLA_CUDA_DEVICES": shards}
+    if _gpu_count() < int(shards):
+        env["SPLA_CUDA_SHARE_DEVICES"] = "1"
+    rc, out = run("test_cuda_backend", "12", env=env)
+    assert rc == 0, out
+    assert "more shard(s) for mxv / vxm" in out and "0 failed" in out, out
+
+
+@pytest.mark.gpu
+@needs_build
+@pytest.mark.parametrize("binary", ["cuda_test_mxv", "cuda_test_vxm"])
+def test_reference_gtests_on_sharded_cuda_backend(binary):
+    env = {"SPLA_CUDA_DEVICES": "2"}
+    if _gpu_count() < 2:
+        env["SPLA_CUDA_SHARE_DEVICES"] = "1"
+    rc, out = run(binary, env=env)
+    assert rc == 0, out[-3000:]
+    assert "[  PASSED  ]" in out and "FAILED" not in out, out[-3000:]
