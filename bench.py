@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--no-vxm", action="store_true", help="skip the push (vxm) block of the line")
     ap.add_argument("--no-bfs", action="store_true", help="skip the BFS push-pull block (BASELINE config 4) of the line")
     ap.add_argument("--bfs-sources", type=int, default=8)
+    ap.add_argument("--no-plugin", action="store_true", help="skip the leg that runs the workload through spla's public C++ API (libspla_cuda_x64.so)")
+    ap.add_argument("--plugin-cpu-steps", type=int, default=1, help="steps of spla's CPU backend inside the plug-in leg (N = 1 only; 0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time vxm / BFS-semiring variants (reported under 'extra')")
     return ap.parse_args()
@@ -492,6 +494,32 @@ def main():
         bfs = bfs_block(be, args, n, Ap, Aj, ones, rank, world)
         del ones
 
+    # ---- through spla's public API with the plug-in (rank 0 drives it; at N > 1 the plug-in itself shards over the N GPUs while the
+    #      other ranks wait at the barrier) ----
+    plugin = None
+    if not args.no_plugin:
+        # the other ranks wait on the HOST (a file flag), not in a collective: an NCCL barrier kernel spinning on their GPUs would take
+        # SMs away from the plug-in's persistent kernels
+        flag = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"spla_b200_plugin_done_{os.environ.get('MASTER_PORT', '0')}")
+        if rank == 0 and os.path.exists(flag):
+            os.remove(flag)
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+        if rank == 0:
+            plugin = plugin_block(args, n, Ap, Aj, world)
+            if world > 1:
+                open(flag, "w").close()
+        elif world > 1:
+            t_wait = time.time()
+            while not os.path.exists(flag) and time.time() - t_wait < 1500:
+                time.sleep(0.2)
+        if world > 1:
+            dist.barrier()
+            if rank == 0 and os.path.exists(flag):
+                os.remove(flag)
+
     # ---- CPU baseline: rank 0, N = 1 only ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -538,6 +566,8 @@ def main():
                                "all-gathered foreign windows on every rank add up to the other ranks' partial sums; asserted before this line is printed. "
                                "Per-element parity at this size: tests/test_gpu_baseline_configs.py (vs the reference CPU backend)"},
         }
+        if plugin:
+            line["plugin"] = plugin
         if vxm:
             line["vxm"] = vxm
         if bfs:
@@ -548,6 +578,55 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def plugin_block(args, n, Ap, Aj, devices):
+    """The same workload through spla's OWN public C++ API with the CUDA backend of this repository plugged in (tools/spla_bench.cpp ->
+    spla_b200/lib/spla_bench, linked to libspla_cuda_x64.so): Matrix::build, the first call with the storage manager's format
+    conversions and the handle build, the steady-state exec_mxv_masked step, spla::pr -- and, at N = 1, spla's CPU backend on the same
+    Matrix object in the same process. devices > 1: the plug-in shards the products over that many GPUs (SPLA_CUDA_DEVICES)."""
+    import numpy as np
+    import torch
+
+    from spla_b200 import graphs
+
+    exe = os.path.join(ROOT, "spla_b200", "lib", "spla_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "spla_b200/lib/spla_bench is not built (needs the reference checkout at build time)"}
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    prefix = os.path.join(tmp, f"spla_b200_bench_{os.getpid()}")
+    nnz = int(Aj.numel())
+    try:
+        deg = (Ap[1:] - Ap[:-1])
+        torch.repeat_interleave(torch.arange(n, device=Ap.device, dtype=torch.int32), deg).cpu().numpy().astype(np.uint32).tofile(prefix + "_Ai.bin")
+        Aj.cpu().numpy().astype(np.uint32).tofile(prefix + "_Aj.bin")
+        graphs.pagerank_values(Ap, 0.85).cpu().numpy().astype(np.float32).tofile(prefix + "_Ax.bin")
+        torch.cuda.empty_cache()
+        env = dict(os.environ)
+        if devices > 1:
+            env["SPLA_CUDA_DEVICES"] = str(devices)
+        cpu_steps = args.plugin_cpu_steps if devices == 1 else 0
+        t0 = time.perf_counter()
+        p = subprocess.run([exe, prefix, str(n), str(nnz), str(max(3, args.steps)), str(cpu_steps), "1"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           text=True, timeout=900)
+        wall = time.perf_counter() - t0
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not line:
+            return {"unavailable": f"spla_bench failed (rc {p.returncode}): {(p.stdout + p.stderr)[-400:]}"}
+        out = json.loads(line[-1])
+        out["devices"] = devices
+        out["wall_s"] = round(wall, 1)
+        out["path"] = ("spla public C++ API (Matrix::build, exec_mxv_masked, exec_v_count_mf, spla::pr) -> Dispatcher -> *_cuda algorithms of "
+                       "spla_b200/src/cuda -> C ABI; vectors stay device-resident between calls, as spla's storage manager keeps them")
+        return out
+    except Exception as ex:  # noqa: BLE001  (a reported leg, never a reason to lose the bench line)
+        return {"unavailable": f"plug-in leg failed: {ex}"}
+    finally:
+        for suf in ("_Ai.bin", "_Aj.bin", "_Ax.bin"):
+            try:
+                os.remove(prefix + suf)
+            except OSError:
+                pass
 
 
 def vxm_alg_bytes(nv, e_f, n_cols, nr, reads_mask=True, reads_ax=True):

@@ -147,6 +147,16 @@ SPLACU_API int splacu_workspace_reset(splacu_workspace ws, void* stream);
  * (uniform frontier values x uniform matrix values under an idempotent add: Ax, vx and the accumulator are never read) */
 SPLACU_API int splacu_workspace_info(splacu_workspace ws, int* struct_only);
 
+/* Ingest: row-major triplets (what Matrix::build leaves in its CpuCoo decoration, reference src/core/tmatrix.hpp:220-253) -> CSR on the
+ * device, replacing the reference's host chain CpuCoo -> CpuLil -> CpuCsr -> AccCsr (src/storage/storage_manager_matrix.hpp:133-159).
+ * d_Ai / d_Aj / d_Ax: nnz triplets in any order; d_Ap: n_rows + 1 row extents (out). Rows already non-decreasing (a loader, a sorted
+ * build): only Ap is computed and d_Aj_out / d_Ax_out MAY be the input arrays themselves (no data movement); otherwise a stable sort
+ * by row fills d_Aj_out / d_Ax_out (which must then be distinct buffers). Inside a row the input order is kept, like the reference's
+ * stable counting sort (src/cpu/cpu_format_coo.hpp:58-76). *was_sorted reports the path taken. Synchronises once (the order check). */
+SPLACU_API int splacu_coo_to_csr(uint32_t n_rows, uint32_t nnz, const uint32_t* d_Ai, const uint32_t* d_Aj, const void* d_Ax,
+                                 uint32_t* d_Ap, uint32_t* d_Aj_out, void* d_Ax_out, splacu_workspace ws, int* was_sorted, void* stream);
+
+
 /* Push (SpMSpV): for every stored (i,x) of sparse v, for (j,a) in row i with select(mask[j]):
  *   acc[j] = first ? mult(x,a) : add(acc[j], mult(x,a));  result = touched (j, acc[j]) ascending in j.
  * Replaces Algo_vxm_masked_cl<T>::execute_sparse (reference src/opencl/cl_vxm.hpp:73-180,

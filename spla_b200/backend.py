@@ -40,7 +40,7 @@ SYMBOLS = [
     "splacu_v_eadd_fdb_dense", "splacu_v_eadd_fdb_sparse_begin", "splacu_v_eadd_fdb_sparse_emit",
     "splacu_v_eadd_dense", "splacu_v_reduce_dense",
     "splacu_mxv_masked_ops", "splacu_vxm_masked_begin_ops", "splacu_v_assign_masked_dense_ops", "splacu_v_assign_masked_sparse_ops",
-    "splacu_profile_enable", "splacu_profile_reset", "splacu_profile_dump",
+    "splacu_coo_to_csr", "splacu_profile_enable", "splacu_profile_reset", "splacu_profile_dump",
     "splacu_vxm_masked_begin_async", "splacu_vxm_masked_begin_finish",
     "splacu_dist_create", "splacu_dist_destroy", "splacu_dist_info", "splacu_dcsr_create", "splacu_dcsr_destroy", "splacu_dcsr_bounds",
     "splacu_dist_mxv_masked", "splacu_dist_vxm_masked_begin", "splacu_dist_vxm_masked_emit",
@@ -116,6 +116,7 @@ def load_library(build_if_missing=True):
         "splacu_v_eadd_dense_op": [i32, pop, u32, vp, vp, vp, vp],
         "splacu_v_eadd_fdb_dense_op": [i32, pop, u32, vp, vp, vp, u32, vp],
         "splacu_v_eadd_fdb_sparse_begin_op": [i32, pop, vp, u32, vp, vp, vp, pu32, vp],
+        "splacu_coo_to_csr": [u32, u32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp],
         "splacu_profile_enable": [i32], "splacu_profile_reset": [], "splacu_profile_dump": [C.c_char_p, i32],
         "splacu_vxm_masked_begin_async": [vp, i32, i32, i32, i32, u32, vp, vp, vp, vp, vp], "splacu_vxm_masked_begin_finish": [vp, pu32, vp],
         "splacu_dist_create": [C.POINTER(vp), i32, C.POINTER(C.c_int)], "splacu_dist_destroy": [vp], "splacu_dist_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
@@ -376,6 +377,19 @@ class Backend:
     def dist_group(self, device_ids):
         """N shards, one per listed device (ids may repeat: shards share a device); device_ids[0] must be this backend's device"""
         return DistGroup(self, device_ids)
+
+    def coo_to_csr(self, n_rows, Ai, Aj, Ax):
+        """device-side ingest: triplets (int32 row ids, int32 column ids, values; any order) -> (Ap, Aj, Ax, was_sorted); sorted rows are
+        converted in place (the returned Aj / Ax are the inputs)"""
+        nnz = Ai.numel()
+        with torch.cuda.stream(self.stream):
+            Ap = torch.empty(n_rows + 1, dtype=torch.int32, device=self.device)
+            oj, ox = torch.empty_like(Aj), torch.empty_like(Ax)
+        flag = C.c_int(0)
+        # first try in place; the unsorted path needs distinct outputs
+        rc = self.lib.splacu_coo_to_csr(n_rows, nnz, _ptr(Ai), _ptr(Aj), _ptr(Ax), _ptr(Ap), _ptr(oj), _ptr(ox), self.ws, C.byref(flag), self.stream_ptr)
+        self._check(rc)
+        return Ap, oj, ox, bool(flag.value)
 
     # ---- format glue ----
     def coo_to_dense(self, n, fill, vi, vx, out=None):

@@ -144,7 +144,11 @@ namespace splacu {
     }
 
     // ---- the kernel ----------------------------------------------------------------------------------
-    template<typename T, typename S, bool MASKED, bool IDX16, int WARPS>
+    // RED: the add is PLUS and r[row] += sum is issued as a reduction at the L2 (red.global.add, no value returned) instead of a
+    // load + add + store: one request and no load latency per segment. The result is the same two-operand rounding, and the order of
+    // the adds onto a row stays fixed (one add per row and launch; launches are ordered), so it remains deterministic. Caveat
+    // (PTX ISA, atom / red .f32 on global memory): subnormal operands and results are flushed to zero.
+    template<typename T, typename S, bool MASKED, bool IDX16, int WARPS, bool RED>
     __global__ void __launch_bounds__(WARPS * 32, 1)
             mxv_seg_kernel(S sr, Select sel, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ flags,
                            const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ chain,
@@ -207,7 +211,7 @@ namespace splacu {
             bool take0 = false;
             if (lane < nfl) {
                 take0 = MASKED ? ((sel_bits[row0 >> 5] >> (row0 & 31u)) & 1u) != 0u : true;
-                old0  = r[row0];
+                if (!RED) old0 = r[row0];
             }
 
             // ---- products of the lane's 16 consecutive entries ----
@@ -295,12 +299,15 @@ namespace splacu {
                     if (o + 64 < nfl) rowC = __ldg(seg_row + base + o + 64);
                     if (o + 32 < nfl) {
                         takeB = MASKED ? ((sel_bits[rowB >> 5] >> (rowB & 31u)) & 1u) != 0u : true;
-                        oldB  = r[rowB];
+                        if (!RED) oldB = r[rowB];
                     }
                     if (o < nfl) {
                         const T sum = s_out[o];
                         if (o == 0 && cont) head[tile] = to_bits(sum);// the row began in an earlier tile: the fix-up adds the chain
-                        else if (takeA) r[rowA] = sr.add(oldA, sum);
+                        else if (takeA) {
+                            if constexpr (RED) atomicAdd(&r[rowA], sum);// result unused: compiles to RED
+                            else r[rowA] = sr.add(oldA, sum);
+                        }
                     }
                     rowA = rowB, takeA = takeB, oldA = oldB, rowB = rowC;
                 }
@@ -347,11 +354,14 @@ namespace splacu {
         }
     }
 
-    template<typename T, typename S, bool MASKED, bool IDX16>
+    template<typename T, typename S, bool MASKED, bool IDX16, bool RED = false>
     static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
                           uint32_t gate_min, cudaStream_t s) {
+        if constexpr (!RED && S::is_static) {
+            if (sr.add_op() == SPLACU_PLUS && get_option(OPT_MXV_RED)) return launch_seg<T, S, MASKED, IDX16, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
+        }
         constexpr int  kW   = IDX16 ? kSegWarps : kSegTailWarps;
-        auto           kern = mxv_seg_kernel<T, S, MASKED, IDX16, kW>;
+        auto           kern = mxv_seg_kernel<T, S, MASKED, IDX16, kW, RED>;
         const uint32_t smem = kW * 512u * 4u + (IDX16 ? ((ph.n_slots + 3u) & ~3u) * 4u : 0u);
         static uint64_t attr_done = 0;// per instantiation, one bit per device: a function attribute belongs to the device it was set on
         const int       dev_bit   = current_device() & 63;

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
+#include <string>
 
 namespace splacu {
 
@@ -36,8 +37,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1, /*mxv_red: class passes of a PLUS semiring add their segment sums onto r with L2 reductions (red.add) instead of load + add + store*/ 0};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct", "mxv_red"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
@@ -181,6 +182,24 @@ int splacu_init(int device) {
     snprintf(g_device_name, sizeof(g_device_name), "%s (sm_%d%d, %d SMs, %.0f GB)", prop.name, prop.major, prop.minor,
              prop.multiProcessorCount, (double) prop.totalGlobalMem / 1e9);
     g_initialised = true;
+    // tuning knobs from the environment, e.g. SPLACU_OPTIONS="mxv_red=1,mxv_phases=3" (the same names splacu_set_option takes)
+    static bool env_done = false;
+    if (!env_done) {
+        env_done = true;
+        if (const char* env = getenv("SPLACU_OPTIONS")) {
+            std::string all(env);
+            size_t      pos = 0;
+            while (pos < all.size()) {
+                size_t end = all.find(',', pos);
+                if (end == std::string::npos) end = all.size();
+                const std::string item = all.substr(pos, end - pos);
+                const size_t      eq   = item.find('=');
+                if (eq != std::string::npos && splacu_set_option(item.substr(0, eq).c_str(), atoll(item.c_str() + eq + 1)) != 0)
+                    fprintf(stderr, "splacu: SPLACU_OPTIONS: unknown option in '%s'\n", item.c_str());
+                pos = end + 1;
+            }
+        }
+    }
     return SPLACU_OK;
 }
 

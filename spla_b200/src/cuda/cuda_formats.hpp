@@ -206,6 +206,47 @@ namespace spla {
         storage.values = n_values;
         SPLACU_CALL(splacu_csr_create(&storage.handle, n_rows, n_cols, n_values, storage.Ap.as_index(), storage.Aj.as_index(), storage.Ax.get(), nullptr));
     }
+    /** triplets on the host -> CSR on the device (device-side ingest, splacu_coo_to_csr) */
+    template<typename T>
+    void cuda_csr_init_from_coo(uint n_rows, uint n_cols, uint n_values, const uint* Ai, const uint* Aj, const T* Ax, CudaCsr<T>& storage) {
+        if (storage.dhandle) {
+            splacu_dcsr_destroy(storage.dhandle);
+            storage.dhandle = nullptr;
+        }
+        if (storage.handle) {
+            splacu_csr_destroy(storage.handle);
+            storage.handle = nullptr;
+        }
+        storage.n_rows = n_rows;
+        storage.n_cols = n_cols;
+        storage.Ap.reserve(std::size_t(n_rows) + 1);
+        storage.Aj.reserve(n_values);
+        storage.Ax.reserve(n_values);
+        CudaBuffer rows;
+        rows.reserve(n_values);
+        SPLACU_CALL(splacu_memcpy_h2d(rows.get(), Ai, std::size_t(n_values) * sizeof(uint), nullptr));
+        SPLACU_CALL(splacu_memcpy_h2d(storage.Aj.get(), Aj, std::size_t(n_values) * sizeof(uint), nullptr));
+        SPLACU_CALL(splacu_memcpy_h2d(storage.Ax.get(), Ax, std::size_t(n_values) * sizeof(T), nullptr));
+        splacu_workspace ws     = get_acc_cuda()->get_workspace();
+        int              sorted = 1;
+        // try in place first: row-sorted triplets only need their row extents
+        int rc = splacu_coo_to_csr(n_rows, n_values, rows.as_index(), storage.Aj.as_index(), storage.Ax.get(), storage.Ap.as_index(), storage.Aj.as_index(),
+                                   storage.Ax.get(), ws, &sorted, nullptr);
+        if (rc != 0) {
+            // unsorted rows: stable sort into fresh buffers
+            CudaBuffer Aj2, Ax2;
+            Aj2.reserve(n_values);
+            Ax2.reserve(n_values);
+            SPLACU_CALL(splacu_coo_to_csr(n_rows, n_values, rows.as_index(), storage.Aj.as_index(), storage.Ax.get(), storage.Ap.as_index(), Aj2.as_index(),
+                                          Ax2.get(), ws, &sorted, nullptr));
+            storage.Aj.swap(Aj2);
+            storage.Ax.swap(Ax2);
+        }
+        SPLACU_CALL(splacu_sync(nullptr));// the sources are pageable host memory owned by the CPU decoration
+        storage.values = n_values;
+        SPLACU_CALL(splacu_csr_create(&storage.handle, n_rows, n_cols, n_values, storage.Ap.as_index(), storage.Aj.as_index(), storage.Ax.get(), nullptr));
+    }
+
     template<typename T>
     void cuda_csr_read(uint n_rows, uint n_values, uint* Ap, uint* Aj, T* Ax, const CudaCsr<T>& storage) {
         SPLACU_CALL(splacu_memcpy_d2h(Ap, storage.Ap.get(), (std::size_t(n_rows) + 1) * sizeof(uint), nullptr));

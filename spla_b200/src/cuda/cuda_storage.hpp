@@ -94,21 +94,14 @@ namespace spla {
             cuda_csr_init(n, s.get_n_cols(), Ap[n], Ap.data(), Aj.data(), Ax.data(), *s.template get<CudaCsr<T>>());
         });
         manager.register_converter(FormatMatrix::CpuCoo, FormatMatrix::AccCsr, [](Storage& s) {
+            // device-side ingest (splacu_coo_to_csr): the triplets are uploaded as they are; row-sorted input (a loader, a sorted
+            // Matrix::build) needs only the row extents, anything else is sorted stably by row on the device -- the entry order inside
+            // a row is the input order, exactly what the host counting sort of the reference chain gives
             auto*             host = s.template get<CpuCoo<T>>();
+            auto*             dev  = s.template get<CudaCsr<T>>();
             const uint        n    = s.get_n_rows();
             const std::size_t nnz  = host->Ai.size();
-            std::vector<uint> Ap(std::size_t(n) + 1, 0);
-            for (std::size_t k = 0; k < nnz; ++k) Ap[host->Ai[k] + 1] += 1;
-            for (uint i = 0; i < n; ++i) Ap[i + 1] += Ap[i];
-            // stable counting sort by row: identical to the input order when the COO is row-sorted (what Matrix::build gets)
-            std::vector<uint> pos(Ap.begin(), Ap.end() - 1), Aj(nnz);
-            std::vector<T>    Ax(nnz);
-            for (std::size_t k = 0; k < nnz; ++k) {
-                const uint q = pos[host->Ai[k]]++;
-                Aj[q]        = host->Aj[k];
-                Ax[q]        = host->Ax[k];
-            }
-            cuda_csr_init(n, s.get_n_cols(), uint(nnz), Ap.data(), Aj.data(), Ax.data(), *s.template get<CudaCsr<T>>());
+            cuda_csr_init_from_coo(n, s.get_n_cols(), uint(nnz), host->Ai.data(), host->Aj.data(), host->Ax.data(), *dev);
         });
         manager.register_converter(FormatMatrix::AccCsr, FormatMatrix::CpuCsr, [](Storage& s) {
             auto* dev  = s.template get<CudaCsr<T>>();

@@ -654,3 +654,35 @@ def test_workspace_reset_after_abandoned_begin(backend, oracle):
     gi, gx = backend.vxm_masked(M, d_vi, d_vx, d_m, "MULT", "PLUS", "EQZERO")
     backend.sync()
     assert np.array_equal(to_np(gi, np.uint32), wi) and np.array_equal(to_np(gx, np.int32), wx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_rows,nnz,order", [(1, 0, "sorted"), (7, 0, "sorted"), (1, 5, "sorted"), (1000, 20000, "sorted"), (1000, 20000, "shuffled"),
+                                              (70001, 300000, "shuffled"), (50, 4000, "reversed"), (300000, 1000, "sorted"), (300000, 1000, "shuffled")])
+def test_ingest_coo_to_csr(backend, n_rows, nnz, order):
+    """splacu_coo_to_csr against a stable host sort by row (reference src/cpu/cpu_format_coo.hpp:58-76: entries of a row keep their
+    input order); sorted input takes the in-place path, anything else the device sort; empty leading / trailing rows included."""
+    rng = np.random.default_rng(nnz + n_rows)
+    lo, hi = (n_rows // 5, n_rows - n_rows // 7) if n_rows > 10 else (0, n_rows)  # leave empty rows at both ends
+    Ai = rng.integers(lo, max(hi, lo + 1), nnz).astype(np.uint32)
+    if order == "sorted":
+        Ai.sort(kind="stable")
+    elif order == "reversed":
+        Ai[::-1].sort(kind="stable")
+    Aj = rng.integers(0, 1 << 20, nnz).astype(np.uint32)
+    Ax = rng.standard_normal(nnz).astype(np.float32)
+    Ap_d, Aj_d, Ax_d, was_sorted = backend.coo_to_csr(n_rows, idx_dev(Ai, backend), idx_dev(Aj, backend), to_dev(Ax, backend))
+    backend.sync()
+    perm = np.argsort(Ai, kind="stable")
+    want_Ap = np.zeros(n_rows + 1, dtype=np.uint32)
+    np.cumsum(np.bincount(Ai, minlength=n_rows), out=want_Ap[1:])
+    assert was_sorted == bool(nnz == 0 or np.all(Ai[1:] >= Ai[:-1]))
+    assert np.array_equal(to_np(Ap_d, np.uint32), want_Ap)
+    assert np.array_equal(to_np(Aj_d, np.uint32), Aj[perm])
+    assert np.array_equal(to_np(Ax_d, np.float32).view(np.uint32), Ax[perm].view(np.uint32))
+    # a row id outside the matrix is refused
+    if nnz:
+        bad = Ai.copy()
+        bad[nnz // 2] = n_rows
+        with pytest.raises(Exception):
+            backend.coo_to_csr(n_rows, idx_dev(bad, backend), idx_dev(Aj, backend), to_dev(Ax, backend))
