@@ -119,6 +119,9 @@ SPLACU_API int splacu_csr_info(splacu_csr M, uint32_t* n_tiles, uint32_t* n_hub)
 /* column-class phases of the pull kernel (hub classes first, the tail class last): *n_phases = number of classes (0 when
  * the matrix is processed in one pass), nnz_per_phase[p] = entries of class p for p < min(*n_phases, cap) */
 SPLACU_API int splacu_csr_phases(splacu_csr M, int* n_phases, uint32_t* nnz_per_phase, int cap);
+/* row classes of the pull kernel's tail (the tail-column entries of the rows with the most of them, kept in column order and
+ * accumulated in shared memory while v streams): number of classes, entries and rows of each (pointers may be NULL) */
+SPLACU_API int splacu_csr_row_classes(splacu_csr M, int* n_classes, uint32_t* nnz_per_class, uint32_t* rows_per_class, int cap);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 

@@ -28,7 +28,7 @@ SEL = {n: i for i, n in enumerate(SEL_OPS)}
 SYMBOLS = [
     "splacu_init", "splacu_finalize", "splacu_device_count", "splacu_device_name", "splacu_sm_count",
     "splacu_default_stream", "splacu_sync", "splacu_last_error", "splacu_launch_count",
-    "splacu_set_option", "splacu_get_option", "splacu_csr_info", "splacu_csr_phases",
+    "splacu_set_option", "splacu_get_option", "splacu_csr_info", "splacu_csr_phases", "splacu_csr_row_classes",
     "splacu_malloc", "splacu_free", "splacu_malloc_host", "splacu_free_host",
     "splacu_memcpy_h2d", "splacu_memcpy_d2h", "splacu_memcpy_d2d", "splacu_fill", "splacu_publish_window",
     "splacu_csr_create", "splacu_csr_destroy", "splacu_mxv_masked",
@@ -86,6 +86,7 @@ def load_library(build_if_missing=True):
         "splacu_sync": [vp], "splacu_launch_count": [C.POINTER(C.c_uint64)],
         "splacu_set_option": [C.c_char_p, C.c_int64], "splacu_get_option": [C.c_char_p, C.POINTER(C.c_int64)],
         "splacu_csr_info": [vp, pu32, pu32], "splacu_csr_phases": [vp, C.POINTER(C.c_int), pu32, i32],
+        "splacu_csr_row_classes": [vp, C.POINTER(C.c_int), pu32, pu32, i32],
         "splacu_malloc": [C.POINTER(vp), sz], "splacu_free": [vp],
         "splacu_malloc_host": [C.POINTER(vp), sz], "splacu_free_host": [vp],
         "splacu_memcpy_h2d": [vp, vp, sz, vp], "splacu_memcpy_d2h": [vp, vp, sz, vp], "splacu_memcpy_d2d": [vp, vp, sz, vp],
@@ -296,7 +297,10 @@ class Backend:
         self._check(self.lib.splacu_csr_info(M.handle, C.byref(nt), C.byref(nh)))
         n_ph, nnz_ph = C.c_int(0), (C.c_uint32 * 32)()
         self._check(self.lib.splacu_csr_phases(M.handle, C.byref(n_ph), nnz_ph, 32))
-        return {"n_tiles": nt.value, "n_hub": nh.value, "phase_nnz": [int(nnz_ph[p]) for p in range(n_ph.value)]}
+        n_rc, nnz_rc, rows_rc = C.c_int(0), (C.c_uint32 * 8)(), (C.c_uint32 * 8)()
+        self._check(self.lib.splacu_csr_row_classes(M.handle, C.byref(n_rc), nnz_rc, rows_rc, 8))
+        return {"n_tiles": nt.value, "n_hub": nh.value, "phase_nnz": [int(nnz_ph[p]) for p in range(n_ph.value)],
+                "row_class_nnz": [int(nnz_rc[q]) for q in range(n_rc.value)], "row_class_rows": [int(rows_rc[q]) for q in range(n_rc.value)]}
 
     def csr(self, n_rows, n_cols, Ap, Aj, Ax):
         with torch.cuda.stream(self.stream):

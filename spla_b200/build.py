@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-diag-suppress", "186",
 ]
-SOURCES = ["runtime.cu", "vector_ops.cu", "mxv_pull.cu", "mxv_seg.cu", "vxm_push.cu", "jit.cu", "user_ops.cu", "dist.cu", "profile.cu", "ingest.cu"]
+SOURCES = ["runtime.cu", "vector_ops.cu", "mxv_pull.cu", "mxv_seg.cu", "mxv_scat.cu", "vxm_push.cu", "jit.cu", "user_ops.cu", "dist.cu", "profile.cu", "ingest.cu"]
 
 
 def nvcc_path():

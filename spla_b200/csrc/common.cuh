@@ -89,6 +89,23 @@ namespace splacu {
     };
     static constexpr int kMaxHubPhases = 16;
 
+    // One ROW class of the tail (mxv_scat.cu): the tail-column entries of the n_slots rows with the most such entries, stored in
+    // COLUMN order in the same lane-blocked 512-entry tiles. The roles of the hub classes are swapped: the segments are columns
+    // (v[seg_col] is read once per segment, in ascending order -- a stream), the 16-bit index is the row's slot in a table of
+    // partial results that the CTA keeps in shared memory, and no gather of v ever leaves the SM for these entries.
+    struct CsrScat {
+        uint32_t  nnz = 0, n_tiles = 0, n_slots = 0, n_segs = 0;
+        uint32_t* rows     = nullptr;// [n_slots] the row of every slot
+        void*     slot     = nullptr;// uint16 [n_tiles * 512] row slot of every entry, lane-blocked
+        uint32_t* Ax       = nullptr;// [n_tiles * 512] lane-blocked
+        uint32_t* flags    = nullptr;// [n_tiles * 16] entry is the last one of its column
+        uint32_t* seg_base = nullptr;// [n_tiles + 1] column segments that end before tile t
+        uint32_t* seg_col  = nullptr;// [n_segs + 1] column of every segment, ascending
+        uint32_t* partial  = nullptr;// [grid * n_slots] per-CTA tables of a call, folded in CTA order by the merge kernel
+        uint32_t  grid     = 0;
+    };
+    static constexpr int kMaxScat = 4;
+
     // storage position of entry e (row order inside a class) in the lane-blocked tile layout: 4-byte items / 2-byte items
     __host__ __device__ __forceinline__ uint32_t seg_pos32(uint32_t e) {
         return (e & ~511u) + (((((e & 15u) >> 2) * 32u) + ((e & 511u) >> 4)) << 2) + (e & 3u);
@@ -100,6 +117,13 @@ namespace splacu {
     struct Csr;
     // mxv_seg.cu: build the segment metadata of a class from its row extents (ph.Ap) and row counts; run all classes
     int seg_build(const Csr* M, CsrPhase& ph, const uint32_t* d_row_count, cudaStream_t s);
+    int seg_structure(const uint32_t* d_ext, const uint32_t* d_count, uint32_t n_units, uint32_t n_tiles, uint32_t** flags, uint32_t** seg_base,
+                      uint32_t** seg_unit, uint32_t* n_segs, cudaStream_t s);
+    // mxv_scat.cu: the row classes of the tail (built from the CSR + the column slot map + the rows chosen by build_phases)
+    int  scat_build(Csr* M, const uint32_t* d_col_slot, const uint32_t* d_rows_sorted, uint32_t n_hub_rows, uint32_t slots_per_class, cudaStream_t s);
+    void scat_free(Csr* M);
+    int  scat_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, void* d_r, const uint32_t* gate,
+                  uint32_t gate_min, cudaStream_t s);
     int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r,
                 uint32_t init_bits, const uint32_t* gate, uint32_t gate_min, cudaStream_t s);
 
@@ -124,6 +148,8 @@ namespace splacu {
         // column-class phases (hub classes first, the tail class last); n_phases == 0: single-pass kernel on Ap / Aj / Ax
         int       n_phases     = 0;
         CsrPhase  phase[kMaxHubPhases + 1];
+        int       n_scat       = 0;      // row classes of the tail (mxv_scat.cu)
+        CsrScat   scat[kMaxScat];
         uint32_t* sel_count    = nullptr;// device counter: rows the mask of the current call selects (chooses the masked path on the device)
         uint32_t* sel_bits     = nullptr;// [n_rows / 32] bit i = select(mask[i]) of the current call: what the class passes read
         // every stored value has the same bit pattern (adjacency matrices): lets the push product run structure-only (vxm_push.cu)
@@ -134,7 +160,7 @@ namespace splacu {
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_MXV_RED, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_MXV_RED, OPT_MXV_ROW_CLASSES, OPT_MXV_ROW_MIN_COUNT, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------

@@ -220,12 +220,13 @@ namespace splacu {
     __global__ void __launch_bounds__(kBlock) phase_scatter_kernel(const uint32_t* __restrict__ Ap, const uint32_t* __restrict__ Aj,
                                                                    const uint32_t* __restrict__ Ax, uint32_t n_rows, const uint32_t* __restrict__ slot,
                                                                    uint32_t slots_per_phase, uint32_t n_hub_phases, uint32_t n_classes,
-                                                                   uint32_t range_shift, PhasePtrs out, int seg) {
+                                                                   uint32_t range_shift, PhasePtrs out, int seg, const uint32_t* __restrict__ row_slot) {
         const uint32_t lane    = threadIdx.x & 31u;
         const uint32_t lt      = (1u << lane) - 1u;
         const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
         for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
             const uint32_t k0 = Ap[row], k1 = Ap[row + 1];
+            const bool     row_class = row_slot && row_slot[row] != 0xffffffffu;// its tail entries live in a row class (mxv_scat.cu)
             uint32_t       off = lane < n_classes ? out.Ap[lane][row] : 0u;// lane q tracks the write position of class q
             for (uint32_t kb = k0; kb < k1; kb += 32) {
                 const uint32_t k  = kb + lane;
@@ -236,7 +237,7 @@ namespace splacu {
                     sl  = slot[col];
                     val = Ax[k];
                 }
-                const uint32_t p = ok ? phase_of(sl, col, slots_per_phase, n_hub_phases, range_shift) : 0xffu;
+                const uint32_t p = (ok && !(row_class && sl == 0xffffffffu)) ? phase_of(sl, col, slots_per_phase, n_hub_phases, range_shift) : 0xffu;
                 for (uint32_t q = 0; q < n_classes; ++q) {
                     const uint32_t m    = __ballot_sync(0xffffffffu, p == q);
                     const uint32_t base = __shfl_sync(0xffffffffu, off, q);
@@ -252,7 +253,27 @@ namespace splacu {
         }
     }
 
+    // rows ranked by their number of tail entries (all tail windows): sort keys, most entries first
+    __global__ void __launch_bounds__(kBlock) tail_keys_kernel(const uint32_t* __restrict__ cnt, size_t stride, uint32_t first_tail, uint32_t n_classes,
+                                                               uint32_t n_rows, uint32_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+        const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+        if (row >= n_rows) return;
+        uint32_t c = 0;
+        for (uint32_t w = first_tail; w < n_classes; ++w) c += cnt[w * stride + row];
+        keys[row] = ~c;
+        ids[row]  = row;
+    }
+    // the rows of the row classes leave the tail classes
+    __global__ void __launch_bounds__(kBlock) tail_clear_kernel(uint32_t* __restrict__ cnt, size_t stride, uint32_t first_tail, uint32_t n_classes,
+                                                                const uint32_t* __restrict__ rows, uint32_t n_hub_rows) {
+        const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+        if (k >= n_hub_rows) return;
+        const uint32_t row = rows[k];
+        for (uint32_t w = first_tail; w < n_classes; ++w) cnt[w * stride + row] = 0u;
+    }
+
     static void free_phases(Csr* M) {
+        scat_free(M);
         for (int p = 0; p < M->n_phases; ++p) {
             CsrPhase& ph = M->phase[p];
             cudaFree(ph.Ap); cudaFree(ph.Aj); cudaFree(ph.Ax); cudaFree(ph.tile_rows); cudaFree(ph.carry);
@@ -274,6 +295,9 @@ namespace splacu {
         uint32_t*      cnt          = nullptr;
         void*          tmp          = nullptr;
         int            rc           = 0;
+        uint32_t *     rkeys = nullptr, *rids = nullptr, *rkeys_out = nullptr, *rows_sorted = nullptr, *row_slot = nullptr;
+        void*          sort_tmp     = nullptr;
+        uint32_t       n_hub_rows   = 0;
 #define PH_CUDA(expr)                                                         \
     do {                                                                      \
         cudaError_t _e = (expr);                                              \
@@ -292,6 +316,35 @@ namespace splacu {
             PH_CUDA(cudaMalloc(&cnt, n_classes * stride * 4));
             PH_CUDA(cudaMemsetAsync(cnt, 0, n_classes * stride * 4, s));
             phase_count_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->n_rows, d_slot, slots_per_phase, n_hub_phases, n_classes, range_shift, cnt);
+            // row classes of the tail (mxv_scat.cu): the rows with the most tail entries hand those entries to a column-ordered copy
+            const uint32_t max_row_classes = (uint32_t) get_option(OPT_MXV_ROW_CLASSES) < (uint32_t) kMaxScat ? (uint32_t) get_option(OPT_MXV_ROW_CLASSES) : (uint32_t) kMaxScat;
+            if (seg && max_row_classes && n_hub_phases) {
+                const uint32_t nr = M->n_rows;
+                size_t         sort_bytes = 0;
+                PH_CUDA(cudaMalloc(&rkeys, (size_t) nr * 4));
+                PH_CUDA(cudaMalloc(&rids, (size_t) nr * 4));
+                PH_CUDA(cudaMalloc(&rkeys_out, (size_t) nr * 4));
+                PH_CUDA(cudaMalloc(&rows_sorted, (size_t) nr * 4));
+                PH_CUDA(cudaMalloc(&row_slot, (size_t) nr * 4));
+                tail_keys_kernel<<<(nr + kBlock - 1) / kBlock, kBlock, 0, s>>>(cnt, stride, n_hub_phases, n_classes, nr, rkeys, rids);
+                PH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, rkeys, rkeys_out, rids, rows_sorted, (int) nr, 0, 32, s));
+                PH_CUDA(cudaMalloc(&sort_tmp, sort_bytes));
+                PH_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, rkeys, rkeys_out, rids, rows_sorted, (int) nr, 0, 32, s));
+                uint32_t cap = max_row_classes * slots_per_phase;
+                if (cap > nr) cap = nr;
+                std::vector<uint32_t> h_keys(cap);
+                PH_CUDA(cudaMemcpyAsync(h_keys.data(), rkeys_out, (size_t) cap * 4, cudaMemcpyDeviceToHost, s));
+                PH_CUDA(cudaStreamSynchronize(s));
+                const uint32_t min_count = (uint32_t) get_option(OPT_MXV_ROW_MIN_COUNT) ? (uint32_t) get_option(OPT_MXV_ROW_MIN_COUNT) : 1u;
+                while (n_hub_rows < cap && ~h_keys[n_hub_rows] >= min_count) ++n_hub_rows;
+                count_launch(5);
+                if (n_hub_rows) {
+                    PH_CUDA(cudaMemsetAsync(row_slot, 0xff, (size_t) nr * 4, s));
+                    hub_slots_kernel<<<(n_hub_rows + kBlock - 1) / kBlock, kBlock, 0, s>>>(rows_sorted, n_hub_rows, row_slot);
+                    tail_clear_kernel<<<(n_hub_rows + kBlock - 1) / kBlock, kBlock, 0, s>>>(cnt, stride, n_hub_phases, n_classes, rows_sorted, n_hub_rows);
+                    count_launch(2);
+                }
+            }
             PH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, cnt, (int) stride, s));
             PH_CUDA(cudaMalloc(&tmp, tmp_bytes));
             for (uint32_t p = 0; p < n_classes; ++p) {
@@ -318,7 +371,7 @@ namespace splacu {
                 }
                 ptrs.Ap[p] = ph.Ap, ptrs.Aj[p] = ph.Aj, ptrs.Ax[p] = ph.Ax;
             }
-            phase_scatter_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->Ax, M->n_rows, d_slot, slots_per_phase, n_hub_phases, n_classes, range_shift, ptrs, seg);
+            phase_scatter_kernel<<<grid_for((size_t) M->n_rows * 32, kBlock, 8), kBlock, 0, s>>>(M->Ap, M->Aj, M->Ax, M->n_rows, d_slot, slots_per_phase, n_hub_phases, n_classes, range_shift, ptrs, seg, n_hub_rows ? row_slot : nullptr);
             count_launch(1);
             for (uint32_t p = 0; p < n_classes; ++p) {
                 CsrPhase& ph = M->phase[p];
@@ -334,11 +387,13 @@ namespace splacu {
             }
             PH_CUDA(cudaStreamSynchronize(s));
             PH_CUDA(cudaGetLastError());
+            if (n_hub_rows && (rc = scat_build(M, d_slot, rows_sorted, n_hub_rows, slots_per_phase, s))) goto done;
         }
     done:
 #undef PH_CUDA
         cudaFree(cnt);
         cudaFree(tmp);
+        cudaFree(rkeys); cudaFree(rids); cudaFree(rkeys_out); cudaFree(rows_sorted); cudaFree(row_slot); cudaFree(sort_tmp);
         if (rc) free_phases(M);
         return rc;
     }

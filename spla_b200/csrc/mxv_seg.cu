@@ -90,7 +90,10 @@ namespace splacu {
         }
     }// namespace
 
-    int seg_build(const Csr* M, CsrPhase& ph, const uint32_t* d_row_count, cudaStream_t s) {
+    // flags / seg_base / segment list of a lane-blocked tile array from the extents of its units (rows of a column class, columns
+    // of a row class): unit u owns entries [d_ext[u], d_ext[u + 1]), d_count[u] = its length. *seg_unit gets n_units + 32 words.
+    int seg_structure(const uint32_t* d_ext, const uint32_t* d_count, uint32_t n_units, uint32_t nt, uint32_t** flags, uint32_t** seg_base,
+                      uint32_t** seg_unit, uint32_t* n_segs, cudaStream_t s) {
         void*     tmp   = nullptr;
         uint32_t* count = nullptr;
         uint32_t* d_num = nullptr;
@@ -104,31 +107,46 @@ namespace splacu {
         }                                                                     \
     } while (0)
         {
+            size_t                              b1 = 0, b2 = 0;
+            thrust::counting_iterator<uint32_t> units(0u);
+            SEG_CUDA(cudaMalloc(flags, (size_t) nt * 16 * 4));
+            SEG_CUDA(cudaMemsetAsync(*flags, 0, (size_t) nt * 16 * 4, s));
+            SEG_CUDA(cudaMalloc(seg_base, ((size_t) nt + 1) * 4));
+            SEG_CUDA(cudaMalloc(&count, ((size_t) nt + 1) * 4));
+            SEG_CUDA(cudaMalloc(&d_num, 4));
+            // every non-empty unit is one segment; + 32: the kernels read the segment list of a tile 32 at a time
+            SEG_CUDA(cudaMalloc(seg_unit, ((size_t) n_units + 32) * 4));
+            SEG_CUDA(cudaMemsetAsync(*seg_unit, 0, ((size_t) n_units + 32) * 4, s));
+            SEG_CUDA(cub::DeviceSelect::Flagged(nullptr, b1, units, d_count, *seg_unit, d_num, (int) n_units, s));
+            SEG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, count, *seg_base, (int) nt + 1, s));
+            SEG_CUDA(cudaMalloc(&tmp, b1 > b2 ? b1 : b2));
+            SEG_CUDA(cub::DeviceSelect::Flagged(tmp, b1, units, d_count, *seg_unit, d_num, (int) n_units, s));
+            seg_flags_kernel<<<(n_units + kBlock - 1) / kBlock, kBlock, 0, s>>>(d_ext, n_units, *flags);
+            seg_tile_count_kernel<<<(nt + 1 + kBlock - 1) / kBlock, kBlock, 0, s>>>(*flags, nt, count);
+            SEG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, b2, count, *seg_base, (int) nt + 1, s));
+            count_launch(4);
+            SEG_CUDA(cudaMemcpyAsync(n_segs, d_num, 4, cudaMemcpyDeviceToHost, s));
+            SEG_CUDA(cudaStreamSynchronize(s));
+            SEG_CUDA(cudaGetLastError());
+        }
+    done:
+        cudaFree(tmp);
+        cudaFree(count);
+        cudaFree(d_num);
+        return rc;
+    }
+
+    int seg_build(const Csr* M, CsrPhase& ph, const uint32_t* d_row_count, cudaStream_t s) {
+        int rc = seg_structure(ph.Ap, d_row_count, M->n_rows, ph.n_tiles, &ph.flags, &ph.seg_base, &ph.seg_row, &ph.n_segs, s);
+        if (rc) return rc;
+        {
             const uint32_t nt = ph.n_tiles;
-            size_t         b1 = 0, b2 = 0;
-            thrust::counting_iterator<uint32_t> rows(0u);
-            SEG_CUDA(cudaMalloc(&ph.flags, (size_t) nt * 16 * 4));
-            SEG_CUDA(cudaMemsetAsync(ph.flags, 0, (size_t) nt * 16 * 4, s));
-            SEG_CUDA(cudaMalloc(&ph.seg_base, ((size_t) nt + 1) * 4));
             SEG_CUDA(cudaMalloc(&ph.chain, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.chain_row, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.head, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.tail, (size_t) nt * 4));
-            SEG_CUDA(cudaMalloc(&count, ((size_t) nt + 1) * 4));
-            SEG_CUDA(cudaMalloc(&d_num, 4));
-            // every non-empty row is one segment; + 32: the kernel reads the rows of a tile 32 at a time
-            SEG_CUDA(cudaMalloc(&ph.seg_row, ((size_t) M->n_rows + 32) * 4));
-            SEG_CUDA(cudaMemsetAsync(ph.seg_row, 0, ((size_t) M->n_rows + 32) * 4, s));
-            SEG_CUDA(cub::DeviceSelect::Flagged(nullptr, b1, rows, d_row_count, ph.seg_row, d_num, (int) M->n_rows, s));
-            SEG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, count, ph.seg_base, (int) nt + 1, s));
-            SEG_CUDA(cudaMalloc(&tmp, b1 > b2 ? b1 : b2));
-            SEG_CUDA(cub::DeviceSelect::Flagged(tmp, b1, rows, d_row_count, ph.seg_row, d_num, (int) M->n_rows, s));
-            seg_flags_kernel<<<(M->n_rows + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, M->n_rows, ph.flags);
-            seg_tile_count_kernel<<<(nt + 1 + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.flags, nt, count);
-            SEG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, b2, count, ph.seg_base, (int) nt + 1, s));
             seg_chain_kernel<<<(nt + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, ph.flags, ph.seg_base, ph.seg_row, nt, ph.chain, ph.chain_row);
-            count_launch(5);
-            SEG_CUDA(cudaMemcpyAsync(&ph.n_segs, d_num, 4, cudaMemcpyDeviceToHost, s));
+            count_launch(1);
             SEG_CUDA(cudaStreamSynchronize(s));
             SEG_CUDA(cudaGetLastError());
             ph.seg = true;
@@ -137,9 +155,6 @@ namespace splacu {
         }
     done:
 #undef SEG_CUDA
-        cudaFree(tmp);
-        cudaFree(count);
-        cudaFree(d_num);
         return rc;
     }
 
@@ -398,6 +413,11 @@ namespace splacu {
         }
         (void) d_mask;
         const int only = (int) get_option(OPT_MXV_PHASE_ONLY);
+        // the row classes of the tail first (mxv_scat.cu): their merge kernels are long done when the tail class needs the SMs
+        if (!only || only > M->n_phases) {
+            const int rc = scat_mxv(M, dtype, op_mult, op_add, sel, d_v, d_r, gate, gate_min, s);
+            if (rc) return rc;
+        }
         return dispatch_dtype(dtype, [&](auto tag) {
             using T       = decltype(tag);
             const T* v    = static_cast<const T*>(d_v);

@@ -37,8 +37,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1, /*mxv_red: class passes of a PLUS semiring add their segment sums onto r with L2 reductions (red.add) instead of load + add + store*/ 0};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct", "mxv_red"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1, /*mxv_red: class passes of a PLUS semiring add their segment sums onto r with L2 reductions (red.add) instead of load + add + store*/ 0, /*mxv_row_classes: row classes of the tail (the tail entries of the rows with the most of them, scattered into a shared-memory table of partial results while v streams)*/ 1, /*mxv_row_min_count: tail entries a row needs to get a slot*/ 64};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct", "mxv_red", "mxv_row_classes", "mxv_row_min_count"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
@@ -297,6 +297,17 @@ int splacu_csr_phases(splacu_csr handle, int* n_phases, uint32_t* nnz_per_phase,
     return SPLACU_OK;
 }
 
+int splacu_csr_row_classes(splacu_csr handle, int* n_classes, uint32_t* nnz_per_class, uint32_t* rows_per_class, int cap) {
+    SPLACU_REQUIRE(handle, "null matrix handle");
+    const Csr* M = reinterpret_cast<const Csr*>(handle);
+    if (n_classes) *n_classes = M->n_scat;
+    for (int q = 0; q < M->n_scat && q < cap; ++q) {
+        if (nnz_per_class) nnz_per_class[q] = M->scat[q].nnz;
+        if (rows_per_class) rows_per_class[q] = M->scat[q].n_slots;
+    }
+    return SPLACU_OK;
+}
+
 int splacu_malloc(void** d_ptr, size_t bytes) {
     SPLACU_CHECK_INIT();
     SPLACU_REQUIRE(d_ptr, "null pointer");
@@ -392,6 +403,7 @@ int splacu_csr_destroy(splacu_csr handle) {
         cudaFree(ph.Ap); cudaFree(ph.Aj); cudaFree(ph.Ax); cudaFree(ph.tile_rows); cudaFree(ph.carry);
         cudaFree(ph.flags); cudaFree(ph.seg_base); cudaFree(ph.seg_row); cudaFree(ph.chain); cudaFree(ph.chain_row); cudaFree(ph.head); cudaFree(ph.tail);
     }
+    scat_free(M);
     cudaGetLastError();
     delete M;
     return SPLACU_OK;

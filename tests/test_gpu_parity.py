@@ -218,7 +218,7 @@ def test_pull_column_class_phases_forced(backend, oracle, dtype, om, oa, osel, s
         backend.set_option("mxv_hub_min_count", min_count)
         M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
         info = backend.csr_info(M)
-        assert len(info["phase_nnz"]) >= 2 and sum(info["phase_nnz"]) == len(Aj), info
+        assert len(info["phase_nnz"]) >= 2 and sum(info["phase_nnz"]) + sum(info["row_class_nnz"]) == len(Aj), info
         assert info["phase_nnz"][0] > 0
     finally:
         backend.set_option("mxv_hub", 1)
@@ -263,7 +263,7 @@ def test_pull_column_class_phases_auto(backend, oracle):
         Ax = cases.rand_values(rng, dtype, len(cols), "unit" if dtype == FLOAT else "small")
         M = make_csr(backend, n, n, Ap, cols, Ax)
         info = backend.csr_info(M)
-        assert len(info["phase_nnz"]) >= 2 and sum(info["phase_nnz"]) == len(cols), info
+        assert len(info["phase_nnz"]) >= 2 and sum(info["phase_nnz"]) + sum(info["row_class_nnz"]) == len(cols), info
         v = cases.rand_values(rng, dtype, n, "unit" if dtype == FLOAT else "small")
         mask = cases.rand_values(rng, dtype, n)
         want = oracle.mxv_masked(dtype, om, oa, osel, Ap, cols, Ax, v, mask, 1, False)
@@ -493,7 +493,7 @@ def test_pull_tail_column_ranges(backend, oracle, dtype, om, oa, osel, seg):
         backend.set_option("mxv_tail_range_log2", 10)
         M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
         info = backend.csr_info(M)
-        assert len(info["phase_nnz"]) == 2 + 3 and sum(info["phase_nnz"]) == len(Aj), info
+        assert len(info["phase_nnz"]) == 2 + 3 and sum(info["phase_nnz"]) + sum(info["row_class_nnz"]) == len(Aj), info
         assert all(x > 0 for x in info["phase_nnz"][2:]), info
     finally:
         backend.set_option("mxv_hub", 1)
@@ -526,7 +526,7 @@ def test_pull_tail_ranges_widen_to_fit(backend):
         backend.set_option("mxv_tail_range_log2", 10)  # 59 windows asked for, 17 classes available
         M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
         info = backend.csr_info(M)
-        assert 2 < len(info["phase_nnz"]) <= 17 and sum(info["phase_nnz"]) == len(Aj), info
+        assert 2 < len(info["phase_nnz"]) <= 17 and sum(info["phase_nnz"]) + sum(info["row_class_nnz"]) == len(Aj), info
     finally:
         backend.set_option("mxv_hub", 1)
         backend.set_option("mxv_phase_slots", 45056)
@@ -686,3 +686,55 @@ def test_ingest_coo_to_csr(backend, n_rows, nnz, order):
         bad[nnz // 2] = n_rows
         with pytest.raises(Exception):
             backend.coo_to_csr(n_rows, idx_dev(bad, backend), idx_dev(Aj, backend), to_dev(Ax, backend))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "MULT", "PLUS", "EQZERO"), (UINT, "BAND", "BOR", "ALWAYS"), (FLOAT, "MULT", "PLUS", "ALWAYS"),
+                                               (FLOAT, "PLUS", "MIN", "NQZERO"), (INT, "LAND", "LOR", "GTZERO"), (FLOAT, "MULT", "PLUS", "NQZERO"),
+                                               (INT, "PLUS", "MAX", "ALWAYS"), (UINT, "MULT", "BXOR", "NQZERO"), (FLOAT, "BONE", "MULT", "ALWAYS"),
+                                               (INT, "MIN", "MULT", "LEZERO")])
+@pytest.mark.parametrize("slots,col_phases,row_classes,row_min", [(4, 1, 1, 1), (16, 2, 4, 2), (64, 3, 2, 1), (1024, 1, 1, 8), (45056, 1, 1, 1)])
+def test_pull_row_classes_forced(backend, oracle, dtype, om, oa, osel, slots, col_phases, row_classes, row_min):
+    """The row classes of the tail (mxv_scat.cu: tail-column entries of the heaviest rows, column-ordered, accumulated with
+    shared-memory atomics while v streams, merged onto r under the mask) forced on small skewed matrices: every op family of the
+    atomic combine (PLUS / MIN / MAX / MULT-by-CAS / logical / bitwise), ragged last tiles, column segments that span tiles (a
+    heavy column), rows that live entirely in a row class, empty rows and unselected rows."""
+    rng = np.random.default_rng(zlib.crc32(repr((dtype, om, oa, slots, row_classes)).encode()))
+    n_rows, n_cols = 2600, 3100
+    kind = "positive" if (om, oa) == ("PLUS", "MIN") else ("unit" if dtype == FLOAT else "small")
+    # skewed rows AND skewed columns; transposing the skewed generator's output makes a few rows very long
+    Ap0, Aj0, Ax0 = _skewed_csr(rng, dtype, n_cols, n_rows, kind)
+    rows0 = np.repeat(np.arange(n_cols), np.diff(Ap0.astype(np.int64)))
+    order = np.lexsort((rows0, Aj0))
+    Aj, Ax = rows0[order].astype(np.uint32), Ax0[order]
+    Ap = np.zeros(n_rows + 1, dtype=np.uint32)
+    Ap[1:] = np.cumsum(np.bincount(Aj0, minlength=n_rows))
+    try:
+        backend.set_option("mxv_hub", 3)
+        backend.set_option("mxv_phase_slots", slots)
+        backend.set_option("mxv_phases", col_phases)
+        backend.set_option("mxv_hub_min_count", 1)
+        backend.set_option("mxv_row_classes", row_classes)
+        backend.set_option("mxv_row_min_count", row_min)
+        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+        info = backend.csr_info(M)
+        assert sum(info["phase_nnz"]) + sum(info["row_class_nnz"]) == len(Aj), info
+        if slots < 45056:
+            assert len(info["row_class_nnz"]) >= 1 and info["row_class_nnz"][0] > 0, info
+        assert len(info["row_class_nnz"]) <= row_classes
+    finally:
+        backend.set_option("mxv_hub", 1)
+        backend.set_option("mxv_phase_slots", 45056)
+        backend.set_option("mxv_phases", 4)
+        backend.set_option("mxv_hub_min_count", 16)
+        backend.set_option("mxv_row_classes", 1)
+        backend.set_option("mxv_row_min_count", 64)
+    for rep in range(3):
+        v = cases.rand_values(rng, dtype, n_cols, kind)
+        mask = cases.rand_values(rng, dtype, n_rows)
+        init = np.float32(3.0e38) if (om, oa) == ("PLUS", "MIN") else (0 if rep == 0 else 3)
+        want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
+        got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
+        backend.sync()
+        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"row classes mxv rep {rep}",
+                      bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
