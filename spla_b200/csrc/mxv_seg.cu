@@ -331,6 +331,183 @@ namespace splacu {
         }
     }
 
+    // ---- the fused kernel: one hub class and one tail class in the same persistent CTAs ---------------------------
+    // Why: the two kinds of pass are bound by DIFFERENT units of the SM. A tail pass saturates the L1 -> L2 request port (one request per
+    // gathered entry, ~1 per clock and SM: 89 % busy, instruction issue 21 %), a hub pass the shared-memory pipe and the issue slots
+    // (LSU wavefronts 63 %, issue 60 %, request port 12 %). Run one after the other they cost the sum; interleaved on the same SM the
+    // slower unit of the mix sets the pace. The price is shared memory: the in-flight gathers of the tail need L1 lines as miss buffers
+    // (tools/l1_hot_bench.cu: full rate down to ~100 KB of L1, a quarter of it at 28 KB), so the fused hub class has a smaller table
+    // (option mxv_fuse_slots).
+    // Roles: a CTA owns a contiguous range of hub tiles and of tail tiles and keeps a shared-memory cursor for each; warps below
+    // tail_warps take tail tiles first, the others hub tiles first, and every warp moves on to the other kind when its own runs out, so
+    // both kinds end together whatever their cost ratio. Both kinds add onto the same rows of r at the same time, hence the segment
+    // sums are combined with atomics (RED at the L2 for PLUS / MIN / MAX / bitwise ops; see atomic_combine): two contributions per row
+    // commute exactly, rows that also get a fix-up or a row-class total see the additions of this kernel in either order (FLOAT PLUS /
+    // MULT: last-bit differences from run to run, far inside the 1e-5 bar).
+    struct SegArgs {
+        const uint32_t* idx;
+        const uint32_t* vals;
+        const uint32_t* flags;
+        const uint32_t* seg_base;
+        const uint32_t* seg_row;
+        const uint32_t* chain;
+        uint32_t*       head;
+        uint32_t*       tail;
+        uint32_t        n_tiles;
+    };
+
+    template<typename T, typename S, bool MASKED, bool IDX16>
+    __device__ __forceinline__ void seg_run_claimed(const S& sr, const SegArgs& a, const T* __restrict__ v, const uint32_t* __restrict__ sel_bits, T* r,
+                                                    const T* s_hub, T* s_out, uint32_t* cursor, uint32_t end, uint32_t lane, uint64_t pol) {
+        constexpr int NI   = IDX16 ? 2 : 4;
+        const uint4*  idx4 = reinterpret_cast<const uint4*>(a.idx);
+        const uint4*  val4 = reinterpret_cast<const uint4*>(a.vals);
+        auto          claim = [&]() {
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(cursor, 1u);
+            return __shfl_sync(0xffffffffu, t, 0);
+        };
+        uint4    xv[4], xi[NI];
+        uint32_t fw = 0, sb0 = 0, sb1 = 0, ch = 0, srow = 0;
+        auto     prefetch = [&](uint32_t t) {
+            if (t >= end) return;
+            sb0 = __ldg(a.seg_base + t);
+            sb1 = __ldg(a.seg_base + t + 1);
+            ch  = __ldg(a.chain + t);
+#pragma unroll
+            for (int h = 0; h < NI; ++h) xi[h] = ld_stream_u4(idx4 + (size_t) t * (NI * 32) + h * 32 + lane, pol);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xv[q] = ld_stream_u4(val4 + (size_t) t * 128 + q * 32 + lane, pol);
+            fw   = __ldg(a.flags + t * 16u + (lane >> 1));
+            srow = __ldg(a.seg_row + sb0 + lane);// padded by 32 rows
+        };
+        uint32_t tile = claim();
+        prefetch(tile);
+        while (tile < end) {
+            const uint32_t next = claim();
+            const uint32_t base = sb0, nfl = sb1 - sb0;
+            const bool     cont = (ch >> 31) != 0u;
+            const uint32_t row0 = srow;
+            const uint32_t fl   = (fw >> ((lane & 1u) * 16u)) & 0xffffu;
+            bool           take0 = false;
+            if (lane < nfl) take0 = MASKED ? ((sel_bits[row0 >> 5] >> (row0 & 31u)) & 1u) != 0u : true;
+
+            T p[16];
+            if (IDX16) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t w[4] = {xi[h].x, xi[h].y, xi[h].z, xi[h].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        p[8 * h + 2 * k]     = s_hub[w[k] & 0xffffu];
+                        p[8 * h + 2 * k + 1] = s_hub[w[k] >> 16];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    p[4 * q + 0] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].x));
+                    p[4 * q + 1] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].y));
+                    p[4 * q + 2] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].z));
+                    p[4 * q + 3] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].w));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                p[4 * q + 0] = sr.mult(from_bits<T>(xv[q].x), p[4 * q + 0]);
+                p[4 * q + 1] = sr.mult(from_bits<T>(xv[q].y), p[4 * q + 1]);
+                p[4 * q + 2] = sr.mult(from_bits<T>(xv[q].z), p[4 * q + 2]);
+                p[4 * q + 3] = sr.mult(from_bits<T>(xv[q].w), p[4 * q + 3]);
+            }
+            prefetch(next);// the slice registers are free again
+
+            const uint32_t cnt  = __popc(fl);
+            uint32_t       incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int) lane >= d) incl += t;
+            }
+            uint32_t k = incl - cnt;
+            T open = sr.identity();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) open = ((fl >> i) & 1u) ? sr.identity() : sr.add(open, p[i]);
+            T    sv = open;
+            bool sf = fl != 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const T    vv = __shfl_up_sync(0xffffffffu, sv, d);
+                const bool ff = __shfl_up_sync(0xffffffffu, (int) sf, d) != 0;
+                if ((int) lane >= d) {
+                    if (!sf) sv = sr.add(vv, sv);
+                    sf = sf || ff;
+                }
+            }
+            T acc = __shfl_up_sync(0xffffffffu, sv, 1);
+            if (lane == 0) acc = sr.identity();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                acc = sr.add(acc, p[i]);
+                if ((fl >> i) & 1u) {
+                    s_out[k] = acc;
+                    ++k;
+                    acc = sr.identity();
+                }
+            }
+            if (lane == 31) a.tail[tile] = to_bits(acc);
+            __syncwarp();
+            {
+                uint32_t rowA = row0, rowB = (nfl > 32u + lane) ? __ldg(a.seg_row + base + 32u + lane) : 0u;
+                bool     takeA = take0;
+                for (uint32_t ob = 0; ob < nfl; ob += 32) {
+                    const uint32_t o = ob + lane;
+                    uint32_t       rowC = 0;
+                    bool           takeB = false;
+                    if (o + 64 < nfl) rowC = __ldg(a.seg_row + base + o + 64);
+                    if (o + 32 < nfl) takeB = MASKED ? ((sel_bits[rowB >> 5] >> (rowB & 31u)) & 1u) != 0u : true;
+                    if (o < nfl) {
+                        const T sum = s_out[o];
+                        if (o == 0 && cont) a.head[tile] = to_bits(sum);
+                        else if (takeA) atomic_combine<T>(sr.add_op(), &r[rowA], sum, sr.identity());
+                    }
+                    rowA = rowB, takeA = takeB, rowB = rowC;
+                }
+            }
+            __syncwarp();
+            tile = next;
+        }
+    }
+
+    template<typename T, typename S, bool MASKED, int WARPS>
+    __global__ void __launch_bounds__(WARPS * 32, 1)
+            mxv_seg_fused_kernel(S sr, SegArgs hub, SegArgs tl, const T* __restrict__ v, const uint32_t* __restrict__ sel_bits, T* r,
+                                 const uint32_t* __restrict__ hub_vals, uint32_t n_slots, uint32_t tail_warps, const uint32_t* __restrict__ gate,
+                                 uint32_t gate_min) {
+        extern __shared__ __align__(16) uint32_t smem[];
+        if (MASKED && gate && *gate < gate_min) return;
+        const uint32_t tid  = threadIdx.x;
+        const uint32_t lane = tid & 31u;
+        const uint32_t warp = tid >> 5;
+        T*             s_out = reinterpret_cast<T*>(smem) + warp * 512;
+        const T*       s_hub = reinterpret_cast<const T*>(smem) + WARPS * 512;
+        uint32_t*      s_cur = smem + WARPS * 512 + ((n_slots + 3u) & ~3u);// [0] hub tiles, [1] tail tiles
+        const uint32_t h0 = (uint32_t) ((uint64_t) hub.n_tiles * blockIdx.x / gridDim.x), h1 = (uint32_t) ((uint64_t) hub.n_tiles * (blockIdx.x + 1) / gridDim.x);
+        const uint32_t t0 = (uint32_t) ((uint64_t) tl.n_tiles * blockIdx.x / gridDim.x), t1 = (uint32_t) ((uint64_t) tl.n_tiles * (blockIdx.x + 1) / gridDim.x);
+        {
+            uint4*       dst = reinterpret_cast<uint4*>(smem + WARPS * 512);
+            const uint4* src = reinterpret_cast<const uint4*>(hub_vals);
+            for (uint32_t i = tid; i < (n_slots + 3u) / 4u; i += WARPS * 32) dst[i] = __ldg(src + i);
+            if (tid == 0) s_cur[0] = h0, s_cur[1] = t0;
+            __syncthreads();
+        }
+        const uint64_t pol = policy_evict_first();
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {// one copy of each body: the instruction cache holds both
+            if ((warp < tail_warps) == (pass == 0)) seg_run_claimed<T, S, MASKED, false>(sr, tl, v, sel_bits, r, s_hub, s_out, s_cur + 1, t1, lane, pol);
+            else seg_run_claimed<T, S, MASKED, true>(sr, hub, v, sel_bits, r, s_hub, s_out, s_cur, h1, lane, pol);
+        }
+    }
+
     // rows that span tiles: r[row] += tail(t0) + tail(t0 + 1) + ... + tail(t - 1) + head(t), left to right; one thread per end
     // tile, the whole warp for chains longer than 4 tiles (hub rows)
     template<typename T, typename S>
@@ -399,6 +576,40 @@ namespace splacu {
         return 0;
     }
 
+    // hub class `ph` and tail class `pt` in one launch (mxv_seg_fused_kernel), then their fix-ups
+    template<typename T, typename S, bool MASKED, int kW>
+    static int launch_fused_w(S sr, Select sel, const Csr* M, const CsrPhase& ph, const CsrPhase& pt, const T* v, const uint32_t* sel_bits, T* r,
+                              const uint32_t* gate, uint32_t gate_min, uint32_t tail_warps, cudaStream_t s) {
+        auto            kern = mxv_seg_fused_kernel<T, S, MASKED, kW>;
+        const uint32_t  smem = kW * 512u * 4u + ((ph.n_slots + 3u) & ~3u) * 4u + 16u;
+        static uint64_t attr_done = 0;
+        const int       dev_bit   = current_device() & 63;
+        if (!((attr_done >> dev_bit) & 1u)) {
+            SPLACU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemMax));
+            attr_done |= (uint64_t) 1 << dev_bit;
+        }
+        const SegArgs ah = {reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head, ph.tail, ph.n_tiles};
+        const SegArgs at = {reinterpret_cast<const uint32_t*>(pt.Aj), pt.Ax, pt.flags, pt.seg_base, pt.seg_row, pt.chain, pt.head, pt.tail, pt.n_tiles};
+        const uint32_t want = (ph.n_tiles + pt.n_tiles + kW - 1) / kW;
+        const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
+        if (tail_warps >= (uint32_t) kW) tail_warps = kW - 1;
+        kern<<<grid, kW * 32, smem, s>>>(sr, ah, at, v, sel_bits, r, M->hub_vals + ph.slot_base, ph.n_slots, tail_warps, gate, gate_min);
+        SPLACU_LAUNCH_CHECK();
+        for (const CsrPhase* q : {&ph, &pt}) {
+            mxv_seg_fixup_kernel<T, S><<<(q->n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, q->chain, q->chain_row, q->head, q->tail, sel_bits, r,
+                                                                                            q->n_tiles, gate, gate_min);
+            SPLACU_LAUNCH_CHECK();
+        }
+        return 0;
+    }
+    // hub class `ph` and tail class `pt` in one launch (mxv_seg_fused_kernel), then their fix-ups
+    template<typename T, typename S, bool MASKED>
+    static int launch_fused(S sr, Select sel, const Csr* M, const CsrPhase& ph, const CsrPhase& pt, const T* v, const uint32_t* sel_bits, T* r,
+                            const uint32_t* gate, uint32_t gate_min, uint32_t tail_warps, cudaStream_t s) {
+        if (get_option(OPT_MXV_FUSE_WARPS) <= 16) return launch_fused_w<T, S, MASKED, 16>(sr, sel, M, ph, pt, v, sel_bits, r, gate, gate_min, tail_warps, s);
+        return launch_fused_w<T, S, MASKED, 20>(sr, sel, M, ph, pt, v, sel_bits, r, gate, gate_min, tail_warps, s);
+    }
+
     int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits,
                 const uint32_t* gate, uint32_t gate_min, cudaStream_t s) {
         // every class accumulates onto r, which starts as init everywhere (unselected and empty rows keep it); with a gate the
@@ -413,7 +624,29 @@ namespace splacu {
         }
         (void) d_mask;
         const int only = (int) get_option(OPT_MXV_PHASE_ONLY);
-        // the row classes of the tail first (mxv_scat.cu): their merge kernels are long done when the tail class needs the SMs
+        // fused launch of the first hub class with the first tail class (option mxv_fuse = warps of a CTA that start on tail tiles)
+        int            fuse_h = -1, fuse_t = -1;
+        const uint32_t fuse_warps = (uint32_t) get_option(OPT_MXV_FUSE);
+        if (fuse_warps && !only && M->n_phases >= 2 && M->phase[0].idx16 && M->phase[0].n_tiles) {
+            for (int p = 1; p < M->n_phases && fuse_t < 0; ++p)
+                if (!M->phase[p].idx16 && M->phase[p].n_tiles) fuse_t = p;
+            if (fuse_t > 0 && (uint32_t) get_option(OPT_MXV_FUSE_WARPS) * 2048u + M->phase[0].n_slots * 4u <= (uint32_t) get_option(OPT_MXV_FUSE_SMEM_KB) * 1024u) fuse_h = 0;
+            else fuse_t = -1;
+        }
+        if (fuse_h >= 0) {
+            const int rc = dispatch_dtype(dtype, [&](auto tag) {
+                using T = decltype(tag);
+                return dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
+                    using S = decltype(sr);
+                    const T* v = static_cast<const T*>(d_v);
+                    T*       r = static_cast<T*>(d_r);
+                    if (sel.reads_mask && gate) return launch_fused<T, S, true>(sr, sel, M, M->phase[fuse_h], M->phase[fuse_t], v, M->sel_bits, r, gate, gate_min, fuse_warps, s);
+                    return launch_fused<T, S, false>(sr, sel, M, M->phase[fuse_h], M->phase[fuse_t], v, nullptr, r, nullptr, 0u, fuse_warps, s);
+                });
+            });
+            if (rc) return rc;
+        }
+        // the row classes of the tail (mxv_scat.cu): their merge kernels are long done when the tail class needs the SMs
         if (!only || only > M->n_phases) {
             const int rc = scat_mxv(M, dtype, op_mult, op_add, sel, d_v, d_r, gate, gate_min, s);
             if (rc) return rc;
@@ -426,7 +659,7 @@ namespace splacu {
                 using S = decltype(sr);
                 for (int p = 0; p < M->n_phases; ++p) {
                     const CsrPhase& ph = M->phase[p];
-                    if (ph.nnz == 0 || (only && only != p + 1)) continue;
+                    if (ph.nnz == 0 || (only && only != p + 1) || p == fuse_h || p == fuse_t) continue;
                     int e;
                     if (sel.reads_mask && gate) e = ph.idx16 ? launch_seg<T, S, true, true>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s) : launch_seg<T, S, true, false>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s);
                     else e = ph.idx16 ? launch_seg<T, S, false, true>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s) : launch_seg<T, S, false, false>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s);
