@@ -277,7 +277,7 @@ namespace splacu {
         for (int p = 0; p < M->n_phases; ++p) {
             CsrPhase& ph = M->phase[p];
             cudaFree(ph.Ap); cudaFree(ph.Aj); cudaFree(ph.Ax); cudaFree(ph.tile_rows); cudaFree(ph.carry);
-            cudaFree(ph.flags); cudaFree(ph.seg_base); cudaFree(ph.seg_row); cudaFree(ph.chain); cudaFree(ph.chain_row); cudaFree(ph.head); cudaFree(ph.tail);
+            cudaFree(ph.flags); cudaFree(ph.meta); cudaFree(ph.seg_base); cudaFree(ph.seg_row); cudaFree(ph.chain); cudaFree(ph.chain_row); cudaFree(ph.head); cudaFree(ph.tail);
             ph = CsrPhase();
         }
         M->n_phases = 0;

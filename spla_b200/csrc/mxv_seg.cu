@@ -27,7 +27,10 @@ namespace splacu {
 
     namespace {
         constexpr int      kBlock    = 256;
-        constexpr int      kSegWarps = 20;// warps per persistent CTA of a hub class (shared-memory gathers)
+        #ifndef SPLACU_SEG_WARPS
+#define SPLACU_SEG_WARPS 20
+#endif
+        constexpr int      kSegWarps = SPLACU_SEG_WARPS;// warps per persistent CTA of a hub class (shared-memory gathers)
 #ifndef SPLACU_SEG_TAIL_WARPS
 #define SPLACU_SEG_TAIL_WARPS 20
 #endif
@@ -88,6 +91,26 @@ namespace splacu {
             chain[t]     = w;
             chain_row[t] = row;
         }
+        // per-lane meta words of the single-pass kernel (a warp per tile): the lane's flags, the number of segments the lower lanes of
+        // the tile close (where its own first segment goes in the warp's slice) and the reach of the lane scan (lanes directly below that
+        // belong to the same open row: lane - max(nearest lane <= it with a flag, 0))
+        __global__ void __launch_bounds__(kBlock) seg_meta_kernel(const uint32_t* __restrict__ flags, uint32_t n_tiles, uint32_t* __restrict__ meta) {
+            const uint32_t lane = threadIdx.x & 31u;
+            const uint32_t t    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+            if (t >= n_tiles) return;
+            const uint32_t fl  = (flags[t * 16u + (lane >> 1)] >> ((lane & 1u) * 16u)) & 0xffffu;
+            const uint32_t cnt = __popc(fl);
+            uint32_t       incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int) lane >= d) incl += x;
+            }
+            const uint32_t has   = __ballot_sync(0xffffffffu, fl != 0u);
+            const uint32_t upto  = has & (0xffffffffu >> (31u - lane));// flagged lanes <= this one
+            const uint32_t start = upto ? 31u - (uint32_t) __clz(upto) : 0u;
+            meta[t * 32u + lane] = fl | ((incl - cnt) << 16) | ((lane - start) << 26);
+        }
     }// namespace
 
     // flags / seg_base / segment list of a lane-blocked tile array from the extents of its units (rows of a column class, columns
@@ -146,7 +169,9 @@ namespace splacu {
             SEG_CUDA(cudaMalloc(&ph.head, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.tail, (size_t) nt * 4));
             seg_chain_kernel<<<(nt + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, ph.flags, ph.seg_base, ph.seg_row, nt, ph.chain, ph.chain_row);
-            count_launch(1);
+            SEG_CUDA(cudaMalloc(&ph.meta, (size_t) nt * 32 * 4));
+            seg_meta_kernel<<<(uint32_t) (((size_t) nt * 32 + kBlock - 1) / kBlock), kBlock, 0, s>>>(ph.flags, nt, ph.meta);
+            count_launch(2);
             SEG_CUDA(cudaStreamSynchronize(s));
             SEG_CUDA(cudaGetLastError());
             ph.seg = true;
@@ -331,66 +356,87 @@ namespace splacu {
         }
     }
 
-    // ---- the fused kernel: one hub class and one tail class in the same persistent CTAs ---------------------------
-    // Why: the two kinds of pass are bound by DIFFERENT units of the SM. A tail pass saturates the L1 -> L2 request port (one request per
-    // gathered entry, ~1 per clock and SM: 89 % busy, instruction issue 21 %), a hub pass the shared-memory pipe and the issue slots
-    // (LSU wavefronts 63 %, issue 60 %, request port 12 %). Run one after the other they cost the sum; interleaved on the same SM the
-    // slower unit of the mix sets the pace. The price is shared memory: the in-flight gathers of the tail need L1 lines as miss buffers
-    // (tools/l1_hot_bench.cu: full rate down to ~100 KB of L1, a quarter of it at 28 KB), so the fused hub class has a smaller table
-    // (option mxv_fuse_slots).
-    // Roles: a CTA owns a contiguous range of hub tiles and of tail tiles and keeps a shared-memory cursor for each; warps below
-    // tail_warps take tail tiles first, the others hub tiles first, and every warp moves on to the other kind when its own runs out, so
-    // both kinds end together whatever their cost ratio. Both kinds add onto the same rows of r at the same time, hence the segment
-    // sums are combined with atomics (RED at the L2 for PLUS / MIN / MAX / bitwise ops; see atomic_combine): two contributions per row
-    // commute exactly, rows that also get a fix-up or a row-class total see the additions of this kernel in either order (FLOAT PLUS /
-    // MULT: last-bit differences from run to run, far inside the 1e-5 bar).
-    struct SegArgs {
-        const uint32_t* idx;
-        const uint32_t* vals;
-        const uint32_t* flags;
-        const uint32_t* seg_base;
-        const uint32_t* seg_row;
-        const uint32_t* chain;
-        uint32_t*       head;
-        uint32_t*       tail;
-        uint32_t        n_tiles;
-    };
+    // ---- version 2 of the class kernel: the same tiles, a third fewer instructions -------------------------------------------
+    // ncu (profiles/r01_ncu_step_v9_summary.txt + the source page of the same report): a hub class pass issues 479 instructions per
+    // 512-entry tile at 60 % of the issue slots with 5 warps per scheduler -- instruction count, not bandwidth, sets its pace. Of the
+    // 479, 176 were the two serial folds (open tail first, then the segment sums with a recomputed shared-memory address per flag),
+    // 75 the two lane scans (segment offsets + segmented sum with its flag scan), 64 the address arithmetic of the 16 table gathers.
+    // Here (1) the segment offset of every lane and the reach of its scan are precomputed (meta word, 128 B per tile), so one
+    // value-only scan of 5 shuffles remains; (2) ONE fold: it starts at the identity, stores every closed segment through a running
+    // shared-memory pointer and leaves the open tail; the carry of the lower lanes is added to the lane's first closed segment afterwards
+    // (one LDS / add / STS); (3) table gathers use 32-bit shared-window addresses (extract, LEA, LDS).
+    // The order of the additions stays fixed (carry + (p0 + p1 + ...) instead of ((carry + p0) + p1) + ...): deterministic.
+    __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+        uint32_t x;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr));
+        return x;
+    }
+    __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory"); }
 
-    template<typename T, typename S, bool MASKED, bool IDX16>
-    __device__ __forceinline__ void seg_run_claimed(const S& sr, const SegArgs& a, const T* __restrict__ v, const uint32_t* __restrict__ sel_bits, T* r,
-                                                    const T* s_hub, T* s_out, uint32_t* cursor, uint32_t end, uint32_t lane, uint64_t pol) {
-        constexpr int NI   = IDX16 ? 2 : 4;
-        const uint4*  idx4 = reinterpret_cast<const uint4*>(a.idx);
-        const uint4*  val4 = reinterpret_cast<const uint4*>(a.vals);
-        auto          claim = [&]() {
-            uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(cursor, 1u);
-            return __shfl_sync(0xffffffffu, t, 0);
-        };
+    template<typename T, typename S, bool MASKED, bool IDX16, int WARPS, bool RED>
+    __global__ void __launch_bounds__(WARPS * 32, 1)
+            mxv_seg2_kernel(S sr, Select sel, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ meta,
+                            const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ chain,
+                            uint32_t* __restrict__ head, uint32_t* __restrict__ tail, const T* __restrict__ v, const uint32_t* __restrict__ sel_bits, T* r,
+                            uint32_t n_tiles, const uint32_t* __restrict__ hub_vals, uint32_t n_slots, const uint32_t* __restrict__ gate,
+                            uint32_t gate_min) {
+        extern __shared__ __align__(16) uint32_t smem[];
+        if (MASKED && gate && *gate < gate_min) return;
+        constexpr int  NI   = IDX16 ? 2 : 4;
+        const uint32_t tid  = threadIdx.x;
+        const uint32_t lane = tid & 31u;
+        const uint32_t warp = tid >> 5;
+        const uint32_t a_out = (uint32_t) __cvta_generic_to_shared(smem) + warp * 2048u;// the warp's slice: segment sums of its tile
+        const uint32_t a_hub = (uint32_t) __cvta_generic_to_shared(smem) + WARPS * 2048u;
+        if (IDX16) {
+            uint4*       dst = reinterpret_cast<uint4*>(smem + WARPS * 512);
+            const uint4* src = reinterpret_cast<const uint4*>(hub_vals);
+            for (uint32_t i = tid; i < (n_slots + 3u) / 4u; i += WARPS * 32) dst[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        const uint64_t pol     = policy_evict_first();
+        const uint32_t n_warps = gridDim.x * WARPS;
+        const uint32_t first   = blockIdx.x * WARPS + warp;
+        const uint4*   idx4    = reinterpret_cast<const uint4*>(idx);
+        const uint4*   val4    = reinterpret_cast<const uint4*>(vals);
+
         uint4    xv[4], xi[NI];
-        uint32_t fw = 0, sb0 = 0, sb1 = 0, ch = 0, srow = 0;
-        auto     prefetch = [&](uint32_t t) {
-            if (t >= end) return;
-            sb0 = __ldg(a.seg_base + t);
-            sb1 = __ldg(a.seg_base + t + 1);
-            ch  = __ldg(a.chain + t);
+        uint32_t mw = 0, sb0 = 0, sb1 = 0, ch = 0, srow = 0;
+        uint32_t q0 = 0, q1 = 0, qc = 0;
+        auto     load_meta = [&](uint32_t t) {
+            if (t < n_tiles) {
+                q0 = __ldg(seg_base + t);
+                q1 = __ldg(seg_base + t + 1);
+                qc = __ldg(chain + t);
+            }
+        };
+        auto prefetch = [&](uint32_t t) {
+            if (t >= n_tiles) return;
+            sb0 = q0, sb1 = q1, ch = qc;
+            load_meta(t + n_warps);
 #pragma unroll
             for (int h = 0; h < NI; ++h) xi[h] = ld_stream_u4(idx4 + (size_t) t * (NI * 32) + h * 32 + lane, pol);
 #pragma unroll
             for (int q = 0; q < 4; ++q) xv[q] = ld_stream_u4(val4 + (size_t) t * 128 + q * 32 + lane, pol);
-            fw   = __ldg(a.flags + t * 16u + (lane >> 1));
-            srow = __ldg(a.seg_row + sb0 + lane);// padded by 32 rows
+            mw   = __ldg(meta + t * 32u + lane);
+            srow = __ldg(seg_row + sb0 + lane);// padded by 32 rows
         };
-        uint32_t tile = claim();
-        prefetch(tile);
-        while (tile < end) {
-            const uint32_t next = claim();
+        load_meta(first);
+        prefetch(first);
+
+        for (uint32_t tile = first; tile < n_tiles; tile += n_warps) {
             const uint32_t base = sb0, nfl = sb1 - sb0;
             const bool     cont = (ch >> 31) != 0u;
             const uint32_t row0 = srow;
-            const uint32_t fl   = (fw >> ((lane & 1u) * 16u)) & 0xffffu;
-            bool           take0 = false;
-            if (lane < nfl) take0 = MASKED ? ((sel_bits[row0 >> 5] >> (row0 & 31u)) & 1u) != 0u : true;
+            const uint32_t fl    = mw & 0xffffu;
+            const uint32_t a_k0  = a_out + ((mw >> 14) & 0xffcu);// byte address of the lane's first segment sum
+            const uint32_t reach = mw >> 26;
+            T    old0  = sr.identity();
+            bool take0 = false;
+            if (lane < nfl) {
+                take0 = MASKED ? ((sel_bits[row0 >> 5] >> (row0 & 31u)) & 1u) != 0u : true;
+                if (!RED) old0 = r[row0];
+            }
 
             T p[16];
             if (IDX16) {
@@ -399,8 +445,8 @@ namespace splacu {
                     const uint32_t w[4] = {xi[h].x, xi[h].y, xi[h].z, xi[h].w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        p[8 * h + 2 * k]     = s_hub[w[k] & 0xffffu];
-                        p[8 * h + 2 * k + 1] = s_hub[w[k] >> 16];
+                        p[8 * h + 2 * k]     = from_bits<T>(lds_u32(a_hub + ((w[k] & 0xffffu) << 2)));
+                        p[8 * h + 2 * k + 1] = from_bits<T>(lds_u32(a_hub + ((w[k] >> 16) << 2)));
                     }
                 }
             } else {
@@ -419,92 +465,60 @@ namespace splacu {
                 p[4 * q + 2] = sr.mult(from_bits<T>(xv[q].z), p[4 * q + 2]);
                 p[4 * q + 3] = sr.mult(from_bits<T>(xv[q].w), p[4 * q + 3]);
             }
-            prefetch(next);// the slice registers are free again
+            prefetch(tile + n_warps);// the slice registers are free again
 
-            const uint32_t cnt  = __popc(fl);
-            uint32_t       incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((int) lane >= d) incl += t;
-            }
-            uint32_t k = incl - cnt;
-            T open = sr.identity();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) open = ((fl >> i) & 1u) ? sr.identity() : sr.add(open, p[i]);
-            T    sv = open;
-            bool sf = fl != 0u;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const T    vv = __shfl_up_sync(0xffffffffu, sv, d);
-                const bool ff = __shfl_up_sync(0xffffffffu, (int) sf, d) != 0;
-                if ((int) lane >= d) {
-                    if (!sf) sv = sr.add(vv, sv);
-                    sf = sf || ff;
-                }
-            }
-            T acc = __shfl_up_sync(0xffffffffu, sv, 1);
-            if (lane == 0) acc = sr.identity();
+            // ---- one fold: closed segments -> the warp's slice (without the carry of the lower lanes), open tail stays in acc ----
+            T        acc = sr.identity();
+            uint32_t a_k = a_k0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 acc = sr.add(acc, p[i]);
                 if ((fl >> i) & 1u) {
-                    s_out[k] = acc;
-                    ++k;
+                    sts_u32(a_k, to_bits(acc));
+                    a_k += 4u;
                     acc = sr.identity();
                 }
             }
-            if (lane == 31) a.tail[tile] = to_bits(acc);
+            // ---- lane scan of the open tails over the lanes of the same open row (reach precomputed) ----
+            T sv = acc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const T vv = __shfl_up_sync(0xffffffffu, sv, d);
+                if (reach >= (uint32_t) d) sv = sr.add(vv, sv);
+            }
+            T carry = __shfl_up_sync(0xffffffffu, sv, 1);
+            if (lane == 0) carry = sr.identity();
+            if (fl) sts_u32(a_k0, to_bits(sr.add(carry, from_bits<T>(lds_u32(a_k0)))));// the lane's first closed segment began in lower lanes
+            if (lane == 31) tail[tile] = to_bits(sv);// what follows the tile's last flag (the whole tile when it has none)
             __syncwarp();
+
+            // ---- hand-over (as version 1) ----
             {
-                uint32_t rowA = row0, rowB = (nfl > 32u + lane) ? __ldg(a.seg_row + base + 32u + lane) : 0u;
+                uint32_t rowA = row0, rowB = (nfl > 32u + lane) ? __ldg(seg_row + base + 32u + lane) : 0u;
                 bool     takeA = take0;
+                T        oldA  = old0;
                 for (uint32_t ob = 0; ob < nfl; ob += 32) {
                     const uint32_t o = ob + lane;
                     uint32_t       rowC = 0;
                     bool           takeB = false;
-                    if (o + 64 < nfl) rowC = __ldg(a.seg_row + base + o + 64);
-                    if (o + 32 < nfl) takeB = MASKED ? ((sel_bits[rowB >> 5] >> (rowB & 31u)) & 1u) != 0u : true;
-                    if (o < nfl) {
-                        const T sum = s_out[o];
-                        if (o == 0 && cont) a.head[tile] = to_bits(sum);
-                        else if (takeA) atomic_combine<T>(sr.add_op(), &r[rowA], sum, sr.identity());
+                    T              oldB  = sr.identity();
+                    if (o + 64 < nfl) rowC = __ldg(seg_row + base + o + 64);
+                    if (o + 32 < nfl) {
+                        takeB = MASKED ? ((sel_bits[rowB >> 5] >> (rowB & 31u)) & 1u) != 0u : true;
+                        if (!RED) oldB = r[rowB];
                     }
-                    rowA = rowB, takeA = takeB, rowB = rowC;
+                    if (o < nfl) {
+                        const T sum = from_bits<T>(lds_u32(a_out + (o << 2)));
+                        if (o == 0 && cont) head[tile] = to_bits(sum);// the row began in an earlier tile: the fix-up adds the chain
+                        else if (takeA) {
+                            if constexpr (RED) atomicAdd(&r[rowA], sum);// result unused: compiles to RED
+                            else r[rowA] = sr.add(oldA, sum);
+                        }
+                    }
+                    rowA = rowB, takeA = takeB, oldA = oldB, rowB = rowC;
                 }
             }
-            __syncwarp();
-            tile = next;
-        }
-    }
-
-    template<typename T, typename S, bool MASKED, int WARPS>
-    __global__ void __launch_bounds__(WARPS * 32, 1)
-            mxv_seg_fused_kernel(S sr, SegArgs hub, SegArgs tl, const T* __restrict__ v, const uint32_t* __restrict__ sel_bits, T* r,
-                                 const uint32_t* __restrict__ hub_vals, uint32_t n_slots, uint32_t tail_warps, const uint32_t* __restrict__ gate,
-                                 uint32_t gate_min) {
-        extern __shared__ __align__(16) uint32_t smem[];
-        if (MASKED && gate && *gate < gate_min) return;
-        const uint32_t tid  = threadIdx.x;
-        const uint32_t lane = tid & 31u;
-        const uint32_t warp = tid >> 5;
-        T*             s_out = reinterpret_cast<T*>(smem) + warp * 512;
-        const T*       s_hub = reinterpret_cast<const T*>(smem) + WARPS * 512;
-        uint32_t*      s_cur = smem + WARPS * 512 + ((n_slots + 3u) & ~3u);// [0] hub tiles, [1] tail tiles
-        const uint32_t h0 = (uint32_t) ((uint64_t) hub.n_tiles * blockIdx.x / gridDim.x), h1 = (uint32_t) ((uint64_t) hub.n_tiles * (blockIdx.x + 1) / gridDim.x);
-        const uint32_t t0 = (uint32_t) ((uint64_t) tl.n_tiles * blockIdx.x / gridDim.x), t1 = (uint32_t) ((uint64_t) tl.n_tiles * (blockIdx.x + 1) / gridDim.x);
-        {
-            uint4*       dst = reinterpret_cast<uint4*>(smem + WARPS * 512);
-            const uint4* src = reinterpret_cast<const uint4*>(hub_vals);
-            for (uint32_t i = tid; i < (n_slots + 3u) / 4u; i += WARPS * 32) dst[i] = __ldg(src + i);
-            if (tid == 0) s_cur[0] = h0, s_cur[1] = t0;
-            __syncthreads();
-        }
-        const uint64_t pol = policy_evict_first();
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {// one copy of each body: the instruction cache holds both
-            if ((warp < tail_warps) == (pass == 0)) seg_run_claimed<T, S, MASKED, false>(sr, tl, v, sel_bits, r, s_hub, s_out, s_cur + 1, t1, lane, pol);
-            else seg_run_claimed<T, S, MASKED, true>(sr, hub, v, sel_bits, r, s_hub, s_out, s_cur, h1, lane, pol);
+            __syncwarp();// the slice is reused by the next tile
         }
     }
 
@@ -546,14 +560,13 @@ namespace splacu {
         }
     }
 
-    template<typename T, typename S, bool MASKED, bool IDX16, bool RED = false>
-    static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
-                          uint32_t gate_min, cudaStream_t s) {
-        if constexpr (!RED && S::is_static) {
-            if (sr.add_op() == SPLACU_PLUS && get_option(OPT_MXV_RED)) return launch_seg<T, S, MASKED, IDX16, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
-        }
-        constexpr int  kW   = IDX16 ? kSegWarps : kSegTailWarps;
-        auto           kern = mxv_seg_kernel<T, S, MASKED, IDX16, kW, RED>;
+    template<typename T, typename S, bool MASKED, bool IDX16, bool RED, int kW, bool V2>
+    static int launch_seg_w(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
+                            uint32_t gate_min, cudaStream_t s) {
+        auto           kern = [] {
+            if constexpr (V2) return mxv_seg2_kernel<T, S, MASKED, IDX16, kW, RED>;
+            else return mxv_seg_kernel<T, S, MASKED, IDX16, kW, RED>;
+        }();
         const uint32_t smem = kW * 512u * 4u + (IDX16 ? ((ph.n_slots + 3u) & ~3u) * 4u : 0u);
         static uint64_t attr_done = 0;// per instantiation, one bit per device: a function attribute belongs to the device it was set on
         const int       dev_bit   = current_device() & 63;
@@ -567,7 +580,7 @@ namespace splacu {
         }
         const uint32_t want = (ph.n_tiles + kW - 1) / kW;
         const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
-        kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
+        kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, V2 ? ph.meta : ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
                                                 ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
         SPLACU_LAUNCH_CHECK();
         mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.chain_row, ph.head, ph.tail, sel_bits, r,
@@ -576,38 +589,23 @@ namespace splacu {
         return 0;
     }
 
-    // hub class `ph` and tail class `pt` in one launch (mxv_seg_fused_kernel), then their fix-ups
-    template<typename T, typename S, bool MASKED, int kW>
-    static int launch_fused_w(S sr, Select sel, const Csr* M, const CsrPhase& ph, const CsrPhase& pt, const T* v, const uint32_t* sel_bits, T* r,
-                              const uint32_t* gate, uint32_t gate_min, uint32_t tail_warps, cudaStream_t s) {
-        auto            kern = mxv_seg_fused_kernel<T, S, MASKED, kW>;
-        const uint32_t  smem = kW * 512u * 4u + ((ph.n_slots + 3u) & ~3u) * 4u + 16u;
-        static uint64_t attr_done = 0;
-        const int       dev_bit   = current_device() & 63;
-        if (!((attr_done >> dev_bit) & 1u)) {
-            SPLACU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemMax));
-            attr_done |= (uint64_t) 1 << dev_bit;
+    template<typename T, typename S, bool MASKED, bool IDX16, bool RED = false>
+    static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
+                          uint32_t gate_min, cudaStream_t s) {
+        if constexpr (!RED && S::is_static) {
+            if (sr.add_op() == SPLACU_PLUS && get_option(OPT_MXV_RED)) return launch_seg<T, S, MASKED, IDX16, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
         }
-        const SegArgs ah = {reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head, ph.tail, ph.n_tiles};
-        const SegArgs at = {reinterpret_cast<const uint32_t*>(pt.Aj), pt.Ax, pt.flags, pt.seg_base, pt.seg_row, pt.chain, pt.head, pt.tail, pt.n_tiles};
-        const uint32_t want = (ph.n_tiles + pt.n_tiles + kW - 1) / kW;
-        const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
-        if (tail_warps >= (uint32_t) kW) tail_warps = kW - 1;
-        kern<<<grid, kW * 32, smem, s>>>(sr, ah, at, v, sel_bits, r, M->hub_vals + ph.slot_base, ph.n_slots, tail_warps, gate, gate_min);
-        SPLACU_LAUNCH_CHECK();
-        for (const CsrPhase* q : {&ph, &pt}) {
-            mxv_seg_fixup_kernel<T, S><<<(q->n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, q->chain, q->chain_row, q->head, q->tail, sel_bits, r,
-                                                                                            q->n_tiles, gate, gate_min);
-            SPLACU_LAUNCH_CHECK();
+        // option mxv_seg_version: 1 = version 1 everywhere, 2 = version 2 for the hub classes, 3 = version 2 for the tail classes too
+        const bool v2 = ph.meta && get_option(OPT_MXV_SEG_VERSION) >= (IDX16 ? 2 : 3);
+        if (!v2) return launch_seg_w<T, S, MASKED, IDX16, RED, IDX16 ? kSegWarps : kSegTailWarps, false>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
+        if constexpr (IDX16) {
+            // 24 warps of 80 registers (one spilled word) when the table leaves room for their slices
+            if (get_option(OPT_MXV_SEG_WARPS) >= 24 && 24u * 2048u + ((ph.n_slots + 3u) & ~3u) * 4u <= kSmemMax)
+                return launch_seg_w<T, S, MASKED, true, RED, 24, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
+            return launch_seg_w<T, S, MASKED, true, RED, kSegWarps, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
+        } else {
+            return launch_seg_w<T, S, MASKED, false, RED, kSegTailWarps, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
         }
-        return 0;
-    }
-    // hub class `ph` and tail class `pt` in one launch (mxv_seg_fused_kernel), then their fix-ups
-    template<typename T, typename S, bool MASKED>
-    static int launch_fused(S sr, Select sel, const Csr* M, const CsrPhase& ph, const CsrPhase& pt, const T* v, const uint32_t* sel_bits, T* r,
-                            const uint32_t* gate, uint32_t gate_min, uint32_t tail_warps, cudaStream_t s) {
-        if (get_option(OPT_MXV_FUSE_WARPS) <= 16) return launch_fused_w<T, S, MASKED, 16>(sr, sel, M, ph, pt, v, sel_bits, r, gate, gate_min, tail_warps, s);
-        return launch_fused_w<T, S, MASKED, 20>(sr, sel, M, ph, pt, v, sel_bits, r, gate, gate_min, tail_warps, s);
     }
 
     int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits,
@@ -624,28 +622,6 @@ namespace splacu {
         }
         (void) d_mask;
         const int only = (int) get_option(OPT_MXV_PHASE_ONLY);
-        // fused launch of the first hub class with the first tail class (option mxv_fuse = warps of a CTA that start on tail tiles)
-        int            fuse_h = -1, fuse_t = -1;
-        const uint32_t fuse_warps = (uint32_t) get_option(OPT_MXV_FUSE);
-        if (fuse_warps && !only && M->n_phases >= 2 && M->phase[0].idx16 && M->phase[0].n_tiles) {
-            for (int p = 1; p < M->n_phases && fuse_t < 0; ++p)
-                if (!M->phase[p].idx16 && M->phase[p].n_tiles) fuse_t = p;
-            if (fuse_t > 0 && (uint32_t) get_option(OPT_MXV_FUSE_WARPS) * 2048u + M->phase[0].n_slots * 4u <= (uint32_t) get_option(OPT_MXV_FUSE_SMEM_KB) * 1024u) fuse_h = 0;
-            else fuse_t = -1;
-        }
-        if (fuse_h >= 0) {
-            const int rc = dispatch_dtype(dtype, [&](auto tag) {
-                using T = decltype(tag);
-                return dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
-                    using S = decltype(sr);
-                    const T* v = static_cast<const T*>(d_v);
-                    T*       r = static_cast<T*>(d_r);
-                    if (sel.reads_mask && gate) return launch_fused<T, S, true>(sr, sel, M, M->phase[fuse_h], M->phase[fuse_t], v, M->sel_bits, r, gate, gate_min, fuse_warps, s);
-                    return launch_fused<T, S, false>(sr, sel, M, M->phase[fuse_h], M->phase[fuse_t], v, nullptr, r, nullptr, 0u, fuse_warps, s);
-                });
-            });
-            if (rc) return rc;
-        }
         // the row classes of the tail (mxv_scat.cu): their merge kernels are long done when the tail class needs the SMs
         if (!only || only > M->n_phases) {
             const int rc = scat_mxv(M, dtype, op_mult, op_add, sel, d_v, d_r, gate, gate_min, s);
@@ -659,7 +635,7 @@ namespace splacu {
                 using S = decltype(sr);
                 for (int p = 0; p < M->n_phases; ++p) {
                     const CsrPhase& ph = M->phase[p];
-                    if (ph.nnz == 0 || (only && only != p + 1) || p == fuse_h || p == fuse_t) continue;
+                    if (ph.nnz == 0 || (only && only != p + 1)) continue;
                     int e;
                     if (sel.reads_mask && gate) e = ph.idx16 ? launch_seg<T, S, true, true>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s) : launch_seg<T, S, true, false>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s);
                     else e = ph.idx16 ? launch_seg<T, S, false, true>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s) : launch_seg<T, S, false, false>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s);

@@ -738,52 +738,3 @@ def test_pull_row_classes_forced(backend, oracle, dtype, om, oa, osel, slots, co
         backend.sync()
         assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"row classes mxv rep {rep}",
                       bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "MULT", "PLUS", "EQZERO"), (UINT, "BAND", "BOR", "ALWAYS"), (FLOAT, "MULT", "PLUS", "ALWAYS"),
-                                               (FLOAT, "PLUS", "MIN", "NQZERO"), (INT, "LAND", "LOR", "GTZERO"), (FLOAT, "MULT", "PLUS", "NQZERO"),
-                                               (INT, "PLUS", "MAX", "ALWAYS"), (UINT, "MULT", "BXOR", "NQZERO"), (FLOAT, "BONE", "MULT", "ALWAYS")])
-@pytest.mark.parametrize("slots,col_phases,row_classes,tail_warps,warps", [(16, 2, 0, 8, 16), (64, 3, 1, 1, 20), (1024, 1, 1, 15, 16), (8, 4, 0, 10, 20)])
-def test_pull_fused_hub_and_tail_classes(backend, oracle, dtype, om, oa, osel, slots, col_phases, row_classes, tail_warps, warps):
-    """mxv_seg_fused_kernel (option mxv_fuse): the first hub class and the first tail class run in the same persistent CTAs, tiles
-    claimed from per-CTA cursors, segment sums combined onto r with atomics. Forced on small skewed matrices with every op family of the
-    atomic combine, both CTA shapes, rows that span tiles in both classes (fix-ups after the fused launch) and unselected rows."""
-    rng = np.random.default_rng(zlib.crc32(repr(("fused", dtype, om, oa, slots, tail_warps)).encode()))
-    n_rows, n_cols = 3000, 2900
-    kind = "positive" if (om, oa) == ("PLUS", "MIN") else ("unit" if dtype == FLOAT else "small")
-    Ap, Aj, Ax = _skewed_csr(rng, dtype, n_rows, n_cols, kind)
-    try:
-        backend.set_option("mxv_hub", 3)
-        backend.set_option("mxv_phase_slots", slots)
-        backend.set_option("mxv_phases", col_phases)
-        backend.set_option("mxv_hub_min_count", 1)
-        backend.set_option("mxv_row_classes", row_classes)
-        backend.set_option("mxv_row_min_count", 4)
-        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
-        info = backend.csr_info(M)
-        assert len(info["phase_nnz"]) >= 2 and info["phase_nnz"][0] > 0 and info["phase_nnz"][-1] > 0, info
-    finally:
-        backend.set_option("mxv_hub", 1)
-        backend.set_option("mxv_phase_slots", 45056)
-        backend.set_option("mxv_phases", 4)
-        backend.set_option("mxv_hub_min_count", 16)
-        backend.set_option("mxv_row_classes", 1)
-        backend.set_option("mxv_row_min_count", 64)
-    try:
-        backend.set_option("mxv_fuse", tail_warps)
-        backend.set_option("mxv_fuse_warps", warps)
-        launches = backend.launch_count()
-        for rep in range(3):
-            v = cases.rand_values(rng, dtype, n_cols, kind)
-            mask = cases.rand_values(rng, dtype, n_rows)
-            init = np.float32(3.0e38) if (om, oa) == ("PLUS", "MIN") else (0 if rep == 0 else 3)
-            want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
-            got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
-            backend.sync()
-            assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"fused classes mxv rep {rep}",
-                          bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
-        assert backend.launch_count() > launches
-    finally:
-        backend.set_option("mxv_fuse", 0)
-        backend.set_option("mxv_fuse_warps", 16)
