@@ -74,7 +74,13 @@ SPLACU_API int         splacu_launch_count(uint64_t* count); /* kernels launched
  * the pull kernel; "mxv_hub_min_count" = references a column needs to earn a hub slot (default 16);
  * "mxv_hub_total" / "mxv_hub_smem" = hub slots in total / staged in shared memory; "mxv_l2_persist" = L2 persisting window
  * on v; "vxm_selbits" = expand large frontiers against a select(mask) bitmap instead of the mask itself; "vxm_struct" = structure-only
- * push for large frontiers whose products are provably one value under an idempotent add (default 1) */
+ * push for large frontiers whose products are provably one value under an idempotent add (default 1);
+ * "mxv_phases" / "mxv_phase_slots" = column classes of the pull product and the slots of one class (4 x 45056);
+ * "mxv_row_classes" / "mxv_row_min_count" = row classes of the tail (1) and the tail entries a row needs for a slot (64);
+ * "mxv_red" (read per call, default 1) = the class passes of a PLUS semiring add their row sums onto r with reductions at the L2
+ * (red.global.add) instead of load + add + store. Integer results are unchanged; FLOAT results keep the same two-operand rounding and
+ * the same fixed order, but red.global.add.f32 flushes subnormal operands and sums to zero (PTX ISA), where the reference keeps
+ * them: set 0 when |r| < 1.2e-38 matters. Also from the environment: SPLACU_OPTIONS="name=value,..." */
 SPLACU_API int         splacu_set_option(const char* name, int64_t value);
 SPLACU_API int         splacu_get_option(const char* name, int64_t* value);
 

@@ -79,8 +79,6 @@ namespace splacu {
         bool      seg       = false;
         uint32_t  n_segs    = 0;             // non-empty rows of the class = row segments
         uint32_t* flags     = nullptr;       // [n_tiles * 16] bit (lane * 16 + i): entry (lane, i) is the last entry of its row
-        uint32_t* meta      = nullptr;       // [n_tiles * 32] per lane: bits 0-15 its flags, 16-25 segments the lower lanes of the tile close,
-                                             //                26-30 how many lanes below belong to the same open row (reach of the lane scan)
         uint32_t* seg_base  = nullptr;       // [n_tiles + 1] segments that end before tile t
         uint32_t* seg_row   = nullptr;       // [n_segs] row of every segment, ascending
         uint32_t* chain     = nullptr;       // [n_tiles] bit 31: the tile starts inside a row of the previous tile; low bits: tiles
@@ -162,7 +160,7 @@ namespace splacu {
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_MXV_RED, OPT_MXV_ROW_CLASSES, OPT_MXV_ROW_MIN_COUNT, OPT_MXV_SEG_VERSION, OPT_MXV_SEG_WARPS, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_MXV_RED, OPT_MXV_ROW_CLASSES, OPT_MXV_ROW_MIN_COUNT, OPT_COUNT };
     int64_t get_option(int opt);
 
     // ---- workspace ------------------------------------------------------------------------

@@ -277,7 +277,7 @@ namespace splacu {
         for (int p = 0; p < M->n_phases; ++p) {
             CsrPhase& ph = M->phase[p];
             cudaFree(ph.Ap); cudaFree(ph.Aj); cudaFree(ph.Ax); cudaFree(ph.tile_rows); cudaFree(ph.carry);
-            cudaFree(ph.flags); cudaFree(ph.meta); cudaFree(ph.seg_base); cudaFree(ph.seg_row); cudaFree(ph.chain); cudaFree(ph.chain_row); cudaFree(ph.head); cudaFree(ph.tail);
+            cudaFree(ph.flags); cudaFree(ph.seg_base); cudaFree(ph.seg_row); cudaFree(ph.chain); cudaFree(ph.chain_row); cudaFree(ph.head); cudaFree(ph.tail);
             ph = CsrPhase();
         }
         M->n_phases = 0;
@@ -1104,6 +1104,7 @@ namespace splacu {
         if (get_option(OPT_MXV_L2_PERSIST) && (size_t) M->nnz * 8 > (size_t) 64 << 20)
             if ((rc = set_persisting_window(v, (size_t) M->n_cols * 4, s))) return rc;
         if (M->n_hub) {
+            SPLACU_PROFILE("splacu/mxv/hub_pack", s);
             mxv_hub_pack_kernel<<<(M->n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->hub_cols, M->n_hub, reinterpret_cast<const uint32_t*>(v), M->hub_vals);
             SPLACU_LAUNCH_CHECK();
         }
@@ -1115,12 +1116,14 @@ namespace splacu {
             if (sel.reads_mask && M->sel_count) {
                 gate     = M->sel_count;
                 gate_min = (uint32_t) ((uint64_t) M->n_rows * (uint64_t) get_option(OPT_MXV_SEG_MIN_DENSITY) / 100u);
+                SPLACU_PROFILE("splacu/mxv/mask_count_fill", s);
                 SPLACU_CUDA(cudaMemsetAsync(M->sel_count, 0, 4, s));
                 mask_count_fill_kernel<T><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count, M->sel_bits, r, init);
                 SPLACU_LAUNCH_CHECK();
             }
             rc = seg_mxv(M, TypeCode<T>::value, sr.mult_op(), sr.add_op(), sel, v, mask, r, to_bits(init), gate, gate_min, s);
             if (rc || !gate) return rc;
+            SPLACU_PROFILE("splacu/mxv/csr_pass_gated", s);
             const TileJob job = {M->Ap, M->Aj, M->Ax, M->nnz, M->n_tiles, M->tile_rows, M->carry, (int) M->vec_ok, nullptr, 0u, 0, gate, gate_min};
             return launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, s);
         }

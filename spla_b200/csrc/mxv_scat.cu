@@ -15,6 +15,7 @@
 // only up to rounding (well inside the 1e-5 bar; integer, MIN / MAX, logical and bitwise results are exact and unaffected).
 #include "common.cuh"
 #include "ops.cuh"
+#include "profile.cuh"
 
 #include <cub/device/device_scan.cuh>
 
@@ -283,6 +284,7 @@ namespace splacu {
                         set_error("mxv: row class of %u slots does not fit in shared memory", sc.n_slots);
                         return (int) SPLACU_E_INVALID;
                     }
+                    SPLACU_PROFILE("splacu/mxv/row_class", s);
                     kern<<<sc.grid, kScatWarps * 32, smem, s>>>(sr, static_cast<const uint32_t*>(sc.slot), sc.Ax, sc.flags, sc.seg_base, sc.seg_col, v, sc.nnz,
                                                                 sc.n_tiles, sc.n_segs, sc.n_slots, sc.partial, gate, gate_min);
                     SPLACU_LAUNCH_CHECK();

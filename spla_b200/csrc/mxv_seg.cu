@@ -18,6 +18,7 @@
 // Rows that span tiles leave head / tail partials; mxv_seg_fixup_kernel chains them left to right.
 #include "common.cuh"
 #include "ops.cuh"
+#include "profile.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
@@ -27,10 +28,7 @@ namespace splacu {
 
     namespace {
         constexpr int      kBlock    = 256;
-        #ifndef SPLACU_SEG_WARPS
-#define SPLACU_SEG_WARPS 20
-#endif
-        constexpr int      kSegWarps = SPLACU_SEG_WARPS;// warps per persistent CTA of a hub class (shared-memory gathers)
+        constexpr int      kSegWarps = 20;// warps per persistent CTA of a hub class (shared-memory gathers)
 #ifndef SPLACU_SEG_TAIL_WARPS
 #define SPLACU_SEG_TAIL_WARPS 20
 #endif
@@ -91,26 +89,6 @@ namespace splacu {
             chain[t]     = w;
             chain_row[t] = row;
         }
-        // per-lane meta words of the single-pass kernel (a warp per tile): the lane's flags, the number of segments the lower lanes of
-        // the tile close (where its own first segment goes in the warp's slice) and the reach of the lane scan (lanes directly below that
-        // belong to the same open row: lane - max(nearest lane <= it with a flag, 0))
-        __global__ void __launch_bounds__(kBlock) seg_meta_kernel(const uint32_t* __restrict__ flags, uint32_t n_tiles, uint32_t* __restrict__ meta) {
-            const uint32_t lane = threadIdx.x & 31u;
-            const uint32_t t    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-            if (t >= n_tiles) return;
-            const uint32_t fl  = (flags[t * 16u + (lane >> 1)] >> ((lane & 1u) * 16u)) & 0xffffu;
-            const uint32_t cnt = __popc(fl);
-            uint32_t       incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((int) lane >= d) incl += x;
-            }
-            const uint32_t has   = __ballot_sync(0xffffffffu, fl != 0u);
-            const uint32_t upto  = has & (0xffffffffu >> (31u - lane));// flagged lanes <= this one
-            const uint32_t start = upto ? 31u - (uint32_t) __clz(upto) : 0u;
-            meta[t * 32u + lane] = fl | ((incl - cnt) << 16) | ((lane - start) << 26);
-        }
     }// namespace
 
     // flags / seg_base / segment list of a lane-blocked tile array from the extents of its units (rows of a column class, columns
@@ -169,9 +147,7 @@ namespace splacu {
             SEG_CUDA(cudaMalloc(&ph.head, (size_t) nt * 4));
             SEG_CUDA(cudaMalloc(&ph.tail, (size_t) nt * 4));
             seg_chain_kernel<<<(nt + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, ph.flags, ph.seg_base, ph.seg_row, nt, ph.chain, ph.chain_row);
-            SEG_CUDA(cudaMalloc(&ph.meta, (size_t) nt * 32 * 4));
-            seg_meta_kernel<<<(uint32_t) (((size_t) nt * 32 + kBlock - 1) / kBlock), kBlock, 0, s>>>(ph.flags, nt, ph.meta);
-            count_launch(2);
+            count_launch(1);
             SEG_CUDA(cudaStreamSynchronize(s));
             SEG_CUDA(cudaGetLastError());
             ph.seg = true;
@@ -356,172 +332,6 @@ namespace splacu {
         }
     }
 
-    // ---- version 2 of the class kernel: the same tiles, a third fewer instructions -------------------------------------------
-    // ncu (profiles/r01_ncu_step_v9_summary.txt + the source page of the same report): a hub class pass issues 479 instructions per
-    // 512-entry tile at 60 % of the issue slots with 5 warps per scheduler -- instruction count, not bandwidth, sets its pace. Of the
-    // 479, 176 were the two serial folds (open tail first, then the segment sums with a recomputed shared-memory address per flag),
-    // 75 the two lane scans (segment offsets + segmented sum with its flag scan), 64 the address arithmetic of the 16 table gathers.
-    // Here (1) the segment offset of every lane and the reach of its scan are precomputed (meta word, 128 B per tile), so one
-    // value-only scan of 5 shuffles remains; (2) ONE fold: it starts at the identity, stores every closed segment through a running
-    // shared-memory pointer and leaves the open tail; the carry of the lower lanes is added to the lane's first closed segment afterwards
-    // (one LDS / add / STS); (3) table gathers use 32-bit shared-window addresses (extract, LEA, LDS).
-    // The order of the additions stays fixed (carry + (p0 + p1 + ...) instead of ((carry + p0) + p1) + ...): deterministic.
-    __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-        uint32_t x;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr));
-        return x;
-    }
-    __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory"); }
-
-    template<typename T, typename S, bool MASKED, bool IDX16, int WARPS, bool RED>
-    __global__ void __launch_bounds__(WARPS * 32, 1)
-            mxv_seg2_kernel(S sr, Select sel, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ meta,
-                            const uint32_t* __restrict__ seg_base, const uint32_t* __restrict__ seg_row, const uint32_t* __restrict__ chain,
-                            uint32_t* __restrict__ head, uint32_t* __restrict__ tail, const T* __restrict__ v, const uint32_t* __restrict__ sel_bits, T* r,
-                            uint32_t n_tiles, const uint32_t* __restrict__ hub_vals, uint32_t n_slots, const uint32_t* __restrict__ gate,
-                            uint32_t gate_min) {
-        extern __shared__ __align__(16) uint32_t smem[];
-        if (MASKED && gate && *gate < gate_min) return;
-        constexpr int  NI   = IDX16 ? 2 : 4;
-        const uint32_t tid  = threadIdx.x;
-        const uint32_t lane = tid & 31u;
-        const uint32_t warp = tid >> 5;
-        const uint32_t a_out = (uint32_t) __cvta_generic_to_shared(smem) + warp * 2048u;// the warp's slice: segment sums of its tile
-        const uint32_t a_hub = (uint32_t) __cvta_generic_to_shared(smem) + WARPS * 2048u;
-        if (IDX16) {
-            uint4*       dst = reinterpret_cast<uint4*>(smem + WARPS * 512);
-            const uint4* src = reinterpret_cast<const uint4*>(hub_vals);
-            for (uint32_t i = tid; i < (n_slots + 3u) / 4u; i += WARPS * 32) dst[i] = __ldg(src + i);
-            __syncthreads();
-        }
-        const uint64_t pol     = policy_evict_first();
-        const uint32_t n_warps = gridDim.x * WARPS;
-        const uint32_t first   = blockIdx.x * WARPS + warp;
-        const uint4*   idx4    = reinterpret_cast<const uint4*>(idx);
-        const uint4*   val4    = reinterpret_cast<const uint4*>(vals);
-
-        uint4    xv[4], xi[NI];
-        uint32_t mw = 0, sb0 = 0, sb1 = 0, ch = 0, srow = 0;
-        uint32_t q0 = 0, q1 = 0, qc = 0;
-        auto     load_meta = [&](uint32_t t) {
-            if (t < n_tiles) {
-                q0 = __ldg(seg_base + t);
-                q1 = __ldg(seg_base + t + 1);
-                qc = __ldg(chain + t);
-            }
-        };
-        auto prefetch = [&](uint32_t t) {
-            if (t >= n_tiles) return;
-            sb0 = q0, sb1 = q1, ch = qc;
-            load_meta(t + n_warps);
-#pragma unroll
-            for (int h = 0; h < NI; ++h) xi[h] = ld_stream_u4(idx4 + (size_t) t * (NI * 32) + h * 32 + lane, pol);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) xv[q] = ld_stream_u4(val4 + (size_t) t * 128 + q * 32 + lane, pol);
-            mw   = __ldg(meta + t * 32u + lane);
-            srow = __ldg(seg_row + sb0 + lane);// padded by 32 rows
-        };
-        load_meta(first);
-        prefetch(first);
-
-        for (uint32_t tile = first; tile < n_tiles; tile += n_warps) {
-            const uint32_t base = sb0, nfl = sb1 - sb0;
-            const bool     cont = (ch >> 31) != 0u;
-            const uint32_t row0 = srow;
-            const uint32_t fl    = mw & 0xffffu;
-            const uint32_t a_k0  = a_out + ((mw >> 14) & 0xffcu);// byte address of the lane's first segment sum
-            const uint32_t reach = mw >> 26;
-            T    old0  = sr.identity();
-            bool take0 = false;
-            if (lane < nfl) {
-                take0 = MASKED ? ((sel_bits[row0 >> 5] >> (row0 & 31u)) & 1u) != 0u : true;
-                if (!RED) old0 = r[row0];
-            }
-
-            T p[16];
-            if (IDX16) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t w[4] = {xi[h].x, xi[h].y, xi[h].z, xi[h].w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        p[8 * h + 2 * k]     = from_bits<T>(lds_u32(a_hub + ((w[k] & 0xffffu) << 2)));
-                        p[8 * h + 2 * k + 1] = from_bits<T>(lds_u32(a_hub + ((w[k] >> 16) << 2)));
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    p[4 * q + 0] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].x));
-                    p[4 * q + 1] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].y));
-                    p[4 * q + 2] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].z));
-                    p[4 * q + 3] = from_bits<T>(ld_gather(reinterpret_cast<const uint32_t*>(v) + xi[q].w));
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                p[4 * q + 0] = sr.mult(from_bits<T>(xv[q].x), p[4 * q + 0]);
-                p[4 * q + 1] = sr.mult(from_bits<T>(xv[q].y), p[4 * q + 1]);
-                p[4 * q + 2] = sr.mult(from_bits<T>(xv[q].z), p[4 * q + 2]);
-                p[4 * q + 3] = sr.mult(from_bits<T>(xv[q].w), p[4 * q + 3]);
-            }
-            prefetch(tile + n_warps);// the slice registers are free again
-
-            // ---- one fold: closed segments -> the warp's slice (without the carry of the lower lanes), open tail stays in acc ----
-            T        acc = sr.identity();
-            uint32_t a_k = a_k0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                acc = sr.add(acc, p[i]);
-                if ((fl >> i) & 1u) {
-                    sts_u32(a_k, to_bits(acc));
-                    a_k += 4u;
-                    acc = sr.identity();
-                }
-            }
-            // ---- lane scan of the open tails over the lanes of the same open row (reach precomputed) ----
-            T sv = acc;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const T vv = __shfl_up_sync(0xffffffffu, sv, d);
-                if (reach >= (uint32_t) d) sv = sr.add(vv, sv);
-            }
-            T carry = __shfl_up_sync(0xffffffffu, sv, 1);
-            if (lane == 0) carry = sr.identity();
-            if (fl) sts_u32(a_k0, to_bits(sr.add(carry, from_bits<T>(lds_u32(a_k0)))));// the lane's first closed segment began in lower lanes
-            if (lane == 31) tail[tile] = to_bits(sv);// what follows the tile's last flag (the whole tile when it has none)
-            __syncwarp();
-
-            // ---- hand-over (as version 1) ----
-            {
-                uint32_t rowA = row0, rowB = (nfl > 32u + lane) ? __ldg(seg_row + base + 32u + lane) : 0u;
-                bool     takeA = take0;
-                T        oldA  = old0;
-                for (uint32_t ob = 0; ob < nfl; ob += 32) {
-                    const uint32_t o = ob + lane;
-                    uint32_t       rowC = 0;
-                    bool           takeB = false;
-                    T              oldB  = sr.identity();
-                    if (o + 64 < nfl) rowC = __ldg(seg_row + base + o + 64);
-                    if (o + 32 < nfl) {
-                        takeB = MASKED ? ((sel_bits[rowB >> 5] >> (rowB & 31u)) & 1u) != 0u : true;
-                        if (!RED) oldB = r[rowB];
-                    }
-                    if (o < nfl) {
-                        const T sum = from_bits<T>(lds_u32(a_out + (o << 2)));
-                        if (o == 0 && cont) head[tile] = to_bits(sum);// the row began in an earlier tile: the fix-up adds the chain
-                        else if (takeA) {
-                            if constexpr (RED) atomicAdd(&r[rowA], sum);// result unused: compiles to RED
-                            else r[rowA] = sr.add(oldA, sum);
-                        }
-                    }
-                    rowA = rowB, takeA = takeB, oldA = oldB, rowB = rowC;
-                }
-            }
-            __syncwarp();// the slice is reused by the next tile
-        }
-    }
-
     // rows that span tiles: r[row] += tail(t0) + tail(t0 + 1) + ... + tail(t - 1) + head(t), left to right; one thread per end
     // tile, the whole warp for chains longer than 4 tiles (hub rows)
     template<typename T, typename S>
@@ -560,13 +370,16 @@ namespace splacu {
         }
     }
 
-    template<typename T, typename S, bool MASKED, bool IDX16, bool RED, int kW, bool V2>
-    static int launch_seg_w(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
-                            uint32_t gate_min, cudaStream_t s) {
-        auto           kern = [] {
-            if constexpr (V2) return mxv_seg2_kernel<T, S, MASKED, IDX16, kW, RED>;
-            else return mxv_seg_kernel<T, S, MASKED, IDX16, kW, RED>;
-        }();
+    template<typename T, typename S, bool MASKED, bool IDX16, bool RED = false>
+    static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
+                          uint32_t gate_min, cudaStream_t s) {
+        // (hub classes only: in the tail class, bound by the L1 -> L2 request port, every reduction is one more request while the
+        //  near-coalesced load + store of r costs a few requests per 32 rows; in the stream the tail pass takes 472 us either way)
+        if constexpr (!RED && S::is_static && IDX16) {
+            if (sr.add_op() == SPLACU_PLUS && get_option(OPT_MXV_RED)) return launch_seg<T, S, MASKED, IDX16, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
+        }
+        constexpr int  kW   = IDX16 ? kSegWarps : kSegTailWarps;
+        auto           kern = mxv_seg_kernel<T, S, MASKED, IDX16, kW, RED>;
         const uint32_t smem = kW * 512u * 4u + (IDX16 ? ((ph.n_slots + 3u) & ~3u) * 4u : 0u);
         static uint64_t attr_done = 0;// per instantiation, one bit per device: a function attribute belongs to the device it was set on
         const int       dev_bit   = current_device() & 63;
@@ -580,32 +393,25 @@ namespace splacu {
         }
         const uint32_t want = (ph.n_tiles + kW - 1) / kW;
         const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
-        kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, V2 ? ph.meta : ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
-                                                ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
-        SPLACU_LAUNCH_CHECK();
-        mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.chain_row, ph.head, ph.tail, sel_bits, r,
-                                                                                        ph.n_tiles, gate, gate_min);
-        SPLACU_LAUNCH_CHECK();
+        // per-launch scopes (splacu_profile_enable): the in-stream time of every class pass -- warm caches, no serialisation, which ncu's
+        // per-kernel replay does not show (the tail pass: 402 us under ncu, 472 us in the stream)
+        static const char* const kLabels[2][kMaxHubPhases + 1] = {
+                {"splacu/mxv/class00", "splacu/mxv/class01", "splacu/mxv/class02", "splacu/mxv/class03", "splacu/mxv/class04", "splacu/mxv/class05", "splacu/mxv/class06", "splacu/mxv/class07", "splacu/mxv/class08", "splacu/mxv/class09", "splacu/mxv/class10", "splacu/mxv/class11", "splacu/mxv/class12", "splacu/mxv/class13", "splacu/mxv/class14", "splacu/mxv/class15", "splacu/mxv/class16"},
+                {"splacu/mxv/fixup00", "splacu/mxv/fixup01", "splacu/mxv/fixup02", "splacu/mxv/fixup03", "splacu/mxv/fixup04", "splacu/mxv/fixup05", "splacu/mxv/fixup06", "splacu/mxv/fixup07", "splacu/mxv/fixup08", "splacu/mxv/fixup09", "splacu/mxv/fixup10", "splacu/mxv/fixup11", "splacu/mxv/fixup12", "splacu/mxv/fixup13", "splacu/mxv/fixup14", "splacu/mxv/fixup15", "splacu/mxv/fixup16"}};
+        const int p = (int) (&ph - M->phase);
+        {
+            SPLACU_PROFILE(kLabels[0][p], s);
+            kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
+                                                    ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
+            SPLACU_LAUNCH_CHECK();
+        }
+        {
+            SPLACU_PROFILE(kLabels[1][p], s);
+            mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.chain_row, ph.head, ph.tail, sel_bits, r,
+                                                                                            ph.n_tiles, gate, gate_min);
+            SPLACU_LAUNCH_CHECK();
+        }
         return 0;
-    }
-
-    template<typename T, typename S, bool MASKED, bool IDX16, bool RED = false>
-    static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
-                          uint32_t gate_min, cudaStream_t s) {
-        if constexpr (!RED && S::is_static) {
-            if (sr.add_op() == SPLACU_PLUS && get_option(OPT_MXV_RED)) return launch_seg<T, S, MASKED, IDX16, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
-        }
-        // option mxv_seg_version: 1 = version 1 everywhere, 2 = version 2 for the hub classes, 3 = version 2 for the tail classes too
-        const bool v2 = ph.meta && get_option(OPT_MXV_SEG_VERSION) >= (IDX16 ? 2 : 3);
-        if (!v2) return launch_seg_w<T, S, MASKED, IDX16, RED, IDX16 ? kSegWarps : kSegTailWarps, false>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
-        if constexpr (IDX16) {
-            // 24 warps of 80 registers (one spilled word) when the table leaves room for their slices
-            if (get_option(OPT_MXV_SEG_WARPS) >= 24 && 24u * 2048u + ((ph.n_slots + 3u) & ~3u) * 4u <= kSmemMax)
-                return launch_seg_w<T, S, MASKED, true, RED, 24, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
-            return launch_seg_w<T, S, MASKED, true, RED, kSegWarps, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
-        } else {
-            return launch_seg_w<T, S, MASKED, false, RED, kSegTailWarps, true>(sr, sel, M, ph, v, sel_bits, r, gate, gate_min, s);
-        }
     }
 
     int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits,
@@ -622,7 +428,7 @@ namespace splacu {
         }
         (void) d_mask;
         const int only = (int) get_option(OPT_MXV_PHASE_ONLY);
-        // the row classes of the tail (mxv_scat.cu): their merge kernels are long done when the tail class needs the SMs
+        // the row classes of the tail first (mxv_scat.cu): their merge kernels are long done when the tail class needs the SMs
         if (!only || only > M->n_phases) {
             const int rc = scat_mxv(M, dtype, op_mult, op_add, sel, d_v, d_r, gate, gate_min, s);
             if (rc) return rc;

@@ -37,8 +37,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1, /*mxv_red: class passes of a PLUS semiring add their segment sums onto r with L2 reductions (red.add) instead of load + add + store*/ 0, /*mxv_row_classes: row classes of the tail (the tail entries of the rows with the most of them, scattered into a shared-memory table of partial results while v streams)*/ 1, /*mxv_row_min_count: tail entries a row needs to get a slot*/ 64, /*mxv_seg_version: 1 = two-pass fold with in-kernel lane scans of the flags, 2 = single-pass fold on the per-lane meta words (precomputed segment offsets and scan reach)*/ 2, /*mxv_seg_warps: warps per CTA of a hub class pass of version 2 (20 or 24)*/ 20};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct", "mxv_red", "mxv_row_classes", "mxv_row_min_count", "mxv_seg_version", "mxv_seg_warps"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1, /*mxv_red: hub class passes of a PLUS semiring add their segment sums onto r with L2 reductions (red.add) instead of load + add + store; FLOAT: red.global.add.f32 flushes subnormal sums to zero (PTX ISA), 0 keeps them*/ 1, /*mxv_row_classes: row classes of the tail (the tail entries of the rows with the most of them, scattered into a shared-memory table of partial results while v streams)*/ 1, /*mxv_row_min_count: tail entries a row needs to get a slot*/ 64};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct", "mxv_red", "mxv_row_classes", "mxv_row_min_count"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
@@ -401,7 +401,7 @@ int splacu_csr_destroy(splacu_csr handle) {
     for (int p = 0; p < M->n_phases; ++p) {
         CsrPhase& ph = M->phase[p];
         cudaFree(ph.Ap); cudaFree(ph.Aj); cudaFree(ph.Ax); cudaFree(ph.tile_rows); cudaFree(ph.carry);
-        cudaFree(ph.flags); cudaFree(ph.meta); cudaFree(ph.seg_base); cudaFree(ph.seg_row); cudaFree(ph.chain); cudaFree(ph.chain_row); cudaFree(ph.head); cudaFree(ph.tail);
+        cudaFree(ph.flags); cudaFree(ph.seg_base); cudaFree(ph.seg_row); cudaFree(ph.chain); cudaFree(ph.chain_row); cudaFree(ph.head); cudaFree(ph.tail);
     }
     scat_free(M);
     cudaGetLastError();

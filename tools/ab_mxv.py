@@ -16,8 +16,7 @@ sys.path.insert(0, ROOT)
 from spla_b200 import graphs  # noqa: E402
 from spla_b200.backend import Backend  # noqa: E402
 
-DEFAULTS = {"mxv_hub": 1, "mxv_phase_slots": 45056, "mxv_phases": 4, "mxv_red": 0, "mxv_row_classes": 1, "mxv_row_min_count": 64, "mxv_fuse": 0,
-            "mxv_fuse_warps": 16, "mxv_fuse_smem_kb": 136, "mxv_tail_range_log2": 24, "mxv_first_slots": 0, "mxv_pdl": 0, "mxv_fixup_merge": 0}
+DEFAULTS = {"mxv_hub": 1, "mxv_phase_slots": 45056, "mxv_phases": 4, "mxv_red": 1, "mxv_row_classes": 1, "mxv_row_min_count": 64, "mxv_tail_range_log2": 24, "mxv_phase_only": 0, "mxv_l2_persist": 0, "mxv_tail_hints": 0}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=24)
@@ -25,6 +24,7 @@ ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--cfg", action="append", default=[])
 ap.add_argument("--select", default="NQZERO")
 ap.add_argument("--out", default=None)
+ap.add_argument("--profile", action="store_true", help="per-launch device times inside the stream (splacu_profile_enable)")
 args = ap.parse_args()
 
 be = Backend(0)
@@ -76,6 +76,15 @@ with torch.cuda.stream(be.stream):
         launches = be.launch_count() - l0
         ms = timeit(lambda: be.mxv_masked(M, v, m, "MULT", "PLUS", args.select, 0.0, out=r))
         be.sync()
+        if args.profile:
+            be.profile(True)
+            for _ in range(args.reps):
+                be.mxv_masked(M, v, m, "MULT", "PLUS", args.select, 0.0, out=r)
+            be.sync()
+            dump = be.profile_dump()
+            be.profile(False)
+            for lab, row in sorted(dump.items()):
+                print(f"    {lab:34s} {1000.0 * row['device_ms'] / max(1, row['calls']):9.2f} us  x {row['calls'] // args.reps}", flush=True)
         if ref is None:
             ref = r.clone()
             err = 0.0
