@@ -20,6 +20,7 @@
 #include "ops.cuh"
 #include "profile.cuh"
 
+#include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -370,6 +371,95 @@ namespace splacu {
         }
     }
 
+    // The fix-ups of ALL classes in one cooperative launch: class by class with a grid barrier in between, so that the additions onto a
+    // row that spans tiles in several classes keep their fixed order (class passes first, then the chains in class order). One launch
+    // and n - 1 grid barriers instead of n dependent launches of ~10 us each between the class passes (in the stream: 60 us of a
+    // 1.33 ms step on RMAT-24, and the same 60 us of the 0.31 ms a rank of an 8-GPU run spends in its kernels).
+    struct FixArgs {
+        const uint32_t* chain;
+        const uint32_t* chain_row;
+        const uint32_t* head;
+        const uint32_t* tail;
+        uint32_t        n_tiles;
+    };
+    struct FixAll {
+        FixArgs c[kMaxHubPhases + 1];
+        int     n;
+    };
+    template<typename T, typename S>
+    __global__ void __launch_bounds__(kBlock) mxv_seg_fixup_all_kernel(S sr, FixAll a, const uint32_t* __restrict__ sel_bits, T* r,
+                                                                       const uint32_t* __restrict__ gate, uint32_t gate_min) {
+        if (gate && *gate < gate_min) return;// uniform over the grid: nobody reaches a barrier
+        cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+        const uint32_t                 lane = threadIdx.x & 31u;
+        for (int p = 0; p < a.n; ++p) {
+            const uint32_t* __restrict__ chain     = a.c[p].chain;
+            const uint32_t* __restrict__ chain_row = a.c[p].chain_row;
+            const uint32_t* __restrict__ head      = a.c[p].head;
+            const uint32_t* __restrict__ tail      = a.c[p].tail;
+            const uint32_t n_tiles = a.c[p].n_tiles;
+            const uint32_t padded  = (n_tiles + 31u) & ~31u;// whole warps iterate together (the long chains are folded by the warp)
+            for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < padded; t += gridDim.x * blockDim.x) {
+                uint32_t len = 0, row = 0;
+                if (t < n_tiles) {
+                    len = chain[t] & 0x7fffffffu;
+                    if (len) {
+                        row = chain_row[t];
+                        if (sel_bits && !((sel_bits[row >> 5] >> (row & 31u)) & 1u)) len = 0;
+                    }
+                }
+                if (len > 0 && len <= 4) {
+                    T acc = from_bits<T>(tail[t - len]);
+                    for (uint32_t u = t - len + 1; u < t; ++u) acc = sr.add(acc, from_bits<T>(tail[u]));
+                    acc    = sr.add(acc, from_bits<T>(head[t]));
+                    r[row] = sr.add(r[row], acc);
+                }
+                uint32_t long_mask = __ballot_sync(0xffffffffu, len > 4);
+                while (long_mask) {
+                    const int src = __ffs(long_mask) - 1;
+                    long_mask &= long_mask - 1;
+                    const uint32_t t1 = __shfl_sync(0xffffffffu, t, src), L = __shfl_sync(0xffffffffu, len, src);
+                    T              acc = sr.identity();
+                    for (uint32_t u = lane; u < L; u += 32) acc = sr.add(acc, from_bits<T>(tail[t1 - L + u]));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc = sr.add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+                    if ((int) lane == src) r[row] = sr.add(r[row], sr.add(acc, from_bits<T>(head[t])));
+                }
+            }
+            if (p + 1 < a.n) grid.sync();
+        }
+    }
+    template<typename T, typename S>
+    static int launch_fixup_all(S sr, const Csr* M, const int* classes, int n, const uint32_t* sel_bits, T* r, const uint32_t* gate, uint32_t gate_min,
+                                cudaStream_t s) {
+        if (n == 0) return 0;
+        FixAll   a;
+        uint32_t most = 0;
+        a.n = n;
+        for (int i = 0; i < n; ++i) {
+            const CsrPhase& ph = M->phase[classes[i]];
+            a.c[i]             = {ph.chain, ph.chain_row, ph.head, ph.tail, ph.n_tiles};
+            if (ph.n_tiles > most) most = ph.n_tiles;
+        }
+        auto       kern = mxv_seg_fixup_all_kernel<T, S>;
+        static int per_sm[64] = {0};// co-resident CTAs per SM, per device
+        const int  dev = current_device() & 63;
+        if (!per_sm[dev]) {
+            int nb = 0;
+            SPLACU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kBlock, 0));
+            per_sm[dev] = nb > 0 ? nb : 1;
+        }
+        uint32_t grid = (most + kBlock - 1) / kBlock;
+        const uint32_t cap = (uint32_t) (per_sm[dev] * sm_count());
+        if (grid > cap) grid = cap;
+        if (grid < 1) grid = 1;
+        SPLACU_PROFILE("splacu/mxv/fixup_all", s);
+        void* args[] = {&sr, &a, (void*) &sel_bits, &r, (void*) &gate, &gate_min};
+        SPLACU_CUDA(cudaLaunchCooperativeKernel((const void*) kern, dim3(grid), dim3(kBlock), args, 0, s));
+        count_launch(1);
+        return 0;
+    }
+
     template<typename T, typename S, bool MASKED, bool IDX16, bool RED = false>
     static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
                           uint32_t gate_min, cudaStream_t s) {
@@ -405,7 +495,7 @@ namespace splacu {
                                                     ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
             SPLACU_LAUNCH_CHECK();
         }
-        {
+        if (!get_option(OPT_MXV_FIXUP_MERGE)) {
             SPLACU_PROFILE(kLabels[1][p], s);
             mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.chain_row, ph.head, ph.tail, sel_bits, r,
                                                                                             ph.n_tiles, gate, gate_min);
@@ -439,14 +529,18 @@ namespace splacu {
             T*       r    = static_cast<T*>(d_r);
             return dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
                 using S = decltype(sr);
+                int ran[kMaxHubPhases + 1], n_ran = 0;
                 for (int p = 0; p < M->n_phases; ++p) {
                     const CsrPhase& ph = M->phase[p];
                     if (ph.nnz == 0 || (only && only != p + 1)) continue;
+                    ran[n_ran++] = p;
                     int e;
                     if (sel.reads_mask && gate) e = ph.idx16 ? launch_seg<T, S, true, true>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s) : launch_seg<T, S, true, false>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s);
                     else e = ph.idx16 ? launch_seg<T, S, false, true>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s) : launch_seg<T, S, false, false>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s);
                     if (e) return e;
                 }
+                if (get_option(OPT_MXV_FIXUP_MERGE))
+                    return launch_fixup_all<T, S>(sr, M, ran, n_ran, (sel.reads_mask && gate) ? M->sel_bits : nullptr, r, gate, gate_min, s);
                 return 0;
             });
         });

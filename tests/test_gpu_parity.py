@@ -716,6 +716,7 @@ def test_pull_row_classes_forced(backend, oracle, dtype, om, oa, osel, slots, co
         backend.set_option("mxv_hub_min_count", 1)
         backend.set_option("mxv_row_classes", row_classes)
         backend.set_option("mxv_row_min_count", row_min)
+        backend.set_option("mxv_row_min_nnz", 0)
         M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
         info = backend.csr_info(M)
         assert sum(info["phase_nnz"]) + sum(info["row_class_nnz"]) == len(Aj), info
@@ -729,6 +730,7 @@ def test_pull_row_classes_forced(backend, oracle, dtype, om, oa, osel, slots, co
         backend.set_option("mxv_hub_min_count", 16)
         backend.set_option("mxv_row_classes", 1)
         backend.set_option("mxv_row_min_count", 64)
+        backend.set_option("mxv_row_min_nnz", 25165824)
     for rep in range(3):
         v = cases.rand_values(rng, dtype, n_cols, kind)
         mask = cases.rand_values(rng, dtype, n_rows)

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from spla_b200 import graphs  # noqa: E402
 from spla_b200.backend import Backend  # noqa: E402
 
-DEFAULTS = {"mxv_hub": 1, "mxv_phase_slots": 45056, "mxv_phases": 4, "mxv_red": 1, "mxv_row_classes": 1, "mxv_row_min_count": 64, "mxv_tail_range_log2": 24, "mxv_phase_only": 0, "mxv_l2_persist": 0, "mxv_tail_hints": 0}
+DEFAULTS = {"mxv_hub": 1, "mxv_phase_slots": 45056, "mxv_phases": 4, "mxv_red": 1, "mxv_row_classes": 1, "mxv_row_min_count": 64, "mxv_tail_range_log2": 24, "mxv_phase_only": 0, "mxv_l2_persist": 0, "mxv_fixup_merge": 1, "mxv_row_min_nnz": 25165824}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=24)
@@ -24,6 +24,7 @@ ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--cfg", action="append", default=[])
 ap.add_argument("--select", default="NQZERO")
 ap.add_argument("--out", default=None)
+ap.add_argument("--shard", type=int, default=1, help="time the first of K nnz-balanced row blocks (what one rank of a K-GPU run holds)")
 ap.add_argument("--profile", action="store_true", help="per-launch device times inside the stream (splacu_profile_enable)")
 args = ap.parse_args()
 
@@ -32,11 +33,18 @@ dev = be.device
 n, Ap, Aj = graphs.rmat(args.scale, 16, seed=2, device=dev)
 Ax = graphs.pagerank_values(Ap, 0.85)
 nnz = Aj.numel()
+n_rows = n
+if args.shard > 1:
+    from spla_b200 import dist as sd
+    bounds = sd.balanced_boundaries(Ap, args.shard)
+    Ap, Aj, Ax = sd.row_slice(Ap, Aj, Ax, bounds[0], bounds[1])
+    n_rows = bounds[1] - bounds[0]
+    nnz = Aj.numel()
 Ap32 = Ap.to(torch.int32)
 v = torch.full((n,), 1.0 / n, device=dev)
-mask = torch.ones(n, device=dev)
+mask = torch.ones(n_rows, device=dev)
 torch.cuda.synchronize()
-alg = 4 * (n + 1) + 4 * n * (args.select != "ALWAYS") + 4 * n + 8 * nnz + 4 * min(n, nnz)
+alg = 4 * (n_rows + 1) + 4 * n_rows * (args.select != "ALWAYS") + 4 * n_rows + 8 * nnz + 4 * min(n, nnz)
 
 
 def timeit(fn):
@@ -55,7 +63,7 @@ def timeit(fn):
 ref = None
 lines = []
 with torch.cuda.stream(be.stream):
-    r = torch.empty(n, device=dev)
+    r = torch.empty(n_rows, device=dev)
     for cfg in args.cfg or [""]:
         opts = dict(DEFAULTS)
         for kv in filter(None, cfg.split(",")):
@@ -67,7 +75,7 @@ with torch.cuda.stream(be.stream):
             except Exception:
                 if val != DEFAULTS.get(k):
                     raise
-        M = be.csr(n, n, Ap32, Aj, Ax)
+        M = be.csr(n_rows, n, Ap32, Aj, Ax)
         info = be.csr_info(M)
         m = None if args.select == "ALWAYS" else mask
         l0 = be.launch_count()
