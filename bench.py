@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PEER_MODE = [False]
+OVERLAP = [False]
 METRIC = "GTEPS of masked mxv/vxm, RMAT-24, 1/2/4/8 B200; % of HBM roofline"
 UNIT = "GTEPS"
 OPS = ("MULT", "PLUS", "NQZERO")
@@ -59,7 +60,7 @@ def workload_config(args, n=None, nnz=None, world=1):
         "workload": f"mxv_masked FLOAT {OPS[0]}/{OPS[1]}/{OPS[2]} all-ones mask (PageRank step, E = nnz) on RMAT scale-{args.scale} "
                     f"edge-factor {args.edge_factor}, symmetrised + dedup + no loops, A[i][j] = 0.85/outdeg(i), v = 1/N",
         "graph": f"rmat-{args.scale}",
-        "parallelism": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, vector in the padded equal-window layout, " + ("windows published to the peers by one kernel of NVLink peer stores + device barrier per step" if PEER_MODE[0] else "one in-place ncclAllGather per step"),
+        "parallelism": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, vector in the padded equal-window layout, " + ("windows published to the peers by one kernel of NVLink peer stores + device barrier per step" if PEER_MODE[0] else (("hub values exchanged first (small all-to-all), the windows travel as peer copies on the copy engines beside the hub class passes of the next step" if OVERLAP[0] == 2 else "hub values exchanged first (small all-to-all), the in-place ncclAllGather of the windows overlaps the hub class passes of the next step") if OVERLAP[0] else "one in-place ncclAllGather per step")),
         "cache": "inputs larger than L2 (CSR >> 126 MB), no flush between iterations",
     }
     if n is not None:
@@ -282,6 +283,20 @@ def main():
     # is within noise of the NCCL call (560 vs 538, 1013 vs 1034 GTEPS: the step is bound by synchronisation, not bytes), so the
     # collective library stays the default.
     peer = None
+    overlap = world > 1 and os.environ.get("SPLA_B200_OVERLAP", "1") == "1" and os.environ.get("SPLA_B200_P2P", "0") != "1"
+    pvecs = None
+    if overlap and os.environ.get("SPLA_B200_OVERLAP_DMA", "1") == "1":
+        try:  # peer-mapped vectors: the windows travel on the copy engines
+            pvecs = [sd.PeerVector(be, n_vec), sd.PeerVector(be, n_vec)]
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                print(f"bench: peer-mapped vectors unavailable ({ex}); the windows travel by ncclAllGather", file=sys.stderr)
+            pvecs = None
+        if world > 1:  # all ranks or none
+            ok = torch.tensor([1 if pvecs else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if not bool(ok.item()):
+                pvecs = None
     if world > 1 and os.environ.get("SPLA_B200_P2P", "0") == "1":
         try:
             pv = [sd.PeerVector(be, n_vec), sd.PeerVector(be, n_vec)]
@@ -295,6 +310,10 @@ def main():
         v, v_next = pv[0].tensor[:n_vec], pv[1].tensor[:n_vec]
         v.fill_(1.0 / n)
         v_next.fill_(1.0 / n)
+    elif pvecs:
+        v, v_next = pvecs[0].tensor[:n_vec], pvecs[1].tensor[:n_vec]
+        v.fill_(1.0 / n)
+        v_next.fill_(1.0 / n)
     else:
         v = torch.full((n_vec,), 1.0 / n, dtype=torch.float32, device=dev)
         v_next = torch.full((n_vec,), 1.0 / n, dtype=torch.float32, device=dev)
@@ -304,7 +323,25 @@ def main():
     csr_info = be.csr_info(M)
     w1 = w0 + (r1 - r0)
 
+    # N > 1 (default): the exchange of step k overlaps the hub class passes of step k + 1 (spla_b200.dist.PipelinedPull: the hub
+    # values travel first in a small all-to-all, the all-gather of the windows runs beside part 1 of the next product).
+    # SPLA_B200_OVERLAP=0: product, then all-gather, strictly one after the other.
+    pp = None
+    if overlap:
+        pp = sd.PipelinedPull(be, M, W, w0, r1 - r0, OPS, 0.0, mask_l,
+                              peers={pvecs[0].tensor.data_ptr(): pvecs[0], pvecs[1].tensor.data_ptr(): pvecs[1]} if pvecs else None)
+        if not pp.enabled:
+            pp = None
+    OVERLAP[0] = (2 if pvecs else 1) if pp is not None else 0
+
+    def finish():
+        if pp:
+            pp.finish()
+
     def step(src, dst):
+        if pp:
+            pp.step(src, dst)
+            return
         be.mxv_masked(M, src, mask_l, *OPS, 0.0, out=dst[w0:w1])
         if peer:
             peer[dst.data_ptr()].publish(w0, r1 - r0)
@@ -329,6 +366,7 @@ def main():
         for _ in range(max(3, args.warmup)):
             step(a, b)
             a, b = b, a
+        finish()
         # ---- timed region: device-resident whole-job throughput ----
         barrier()
         sampler = ClockSampler(local_rank)
@@ -340,6 +378,7 @@ def main():
         for _ in range(args.steps):
             step(a, b)
             a, b = b, a
+        finish()  # the last exchange is inside the timed region
         e1.record(be.stream)
         barrier()
         ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
@@ -370,6 +409,7 @@ def main():
         a.fill_(1.0 / n)
         b.zero_()  # the padding of the windows stays 0 on every rank
         step(a, b)
+        finish()
         be.sync()
         sums = torch.stack([b[w0:w1].double().sum(), Ax_l.double().sum() / n,
                             (b[:w0].double().sum() + b[w1:].double().sum()) if world > 1 else torch.zeros((), dtype=torch.float64, device=dev)])

@@ -142,6 +142,23 @@ SPLACU_API int splacu_mxv_masked(splacu_csr M, int dtype, int op_mult, int op_ad
                                  const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits,
                                  int early_exit, void* stream);
 
+/* The pull product in two parts, for callers that assemble v from several owners (row-sharded multi-GPU runs): the entries of
+ * the hub column classes read only the n_hub most referenced elements of v, so their passes can start as soon as THOSE values have
+ * arrived, while the rest of v is still in flight.
+ *   SPLACU_PART_PROLOGUE  r = init / the mask pass (reads nothing of v: can run before anything has arrived)
+ *   SPLACU_PART_HUB       the hub classes. d_hub_vals[i] = v[hub_cols[i]] (splacu_csr_hub_cols) if the caller has gathered them, else
+ *                         NULL and d_v is read. May be combined with the prologue (PROLOGUE | HUB).
+ *   SPLACU_PART_REST      everything that reads v itself (row classes, tail classes, the mask-first CSR pass for sparse masks) and
+ *                         the fix-ups. For matrices without column classes this is the whole product, the other parts are no-ops.
+ * All parts on the same stream in this order, same ops / mask / r / init; op_add associative + commutative, no early exit.
+ * The result equals splacu_mxv_masked up to the order in which the classes add onto r (FLOAT PLUS / MULT: rounding). */
+#define SPLACU_PART_HUB 1
+#define SPLACU_PART_REST 2
+#define SPLACU_PART_PROLOGUE 4
+SPLACU_API int splacu_csr_hub_cols(splacu_csr M, uint32_t* n_hub, const uint32_t** d_cols);
+SPLACU_API int splacu_mxv_masked_part(splacu_csr M, int dtype, int op_mult, int op_add, int op_select, const void* d_v, const void* d_hub_vals,
+                                      const void* d_mask, void* d_r, uint32_t init_bits, int part, void* stream);
+
 /* Per-vector-length scratch for vxm / compaction (dense accumulator, touched bitmap, scan buffers).
  * Replaces the temp linear allocator + counters of reference src/opencl/cl_alloc_linear.hpp, cl_counter.hpp:42-84. */
 typedef struct splacu_workspace_t* splacu_workspace;
@@ -223,6 +240,9 @@ SPLACU_API int splacu_v_assign_masked_sparse(int dtype, int op_assign, int op_se
 /* structure-only form of a dense vector, for the frontier exchange of a multi-GPU traversal ("all-gather an n-bit
  * bitmap", 2 MB instead of 64 MB at scale 24): bit i of d_bits = op_select(v[i]) (ceil(n / 32) words, trailing bits 0), and back:
  * out[i] = bit i ? one_bits : zero_bits. No reference counterpart (the reference is single-device). */
+/* d_dst[k] = d_src[d_idx[k]] / d_dst[d_idx[k]] = d_src[k] for k < n, 4-byte elements (the hub-value exchange of the two-part product) */
+SPLACU_API int splacu_v_gather(uint32_t n, const uint32_t* d_idx, const void* d_src, void* d_dst, void* stream);
+SPLACU_API int splacu_v_scatter(uint32_t n, const uint32_t* d_idx, const void* d_src, void* d_dst, uint32_t n_dst, void* stream);
 SPLACU_API int splacu_v_pack_bits(int dtype, int op_select, uint32_t n, const void* d_v, uint32_t* d_bits, void* stream);
 SPLACU_API int splacu_v_unpack_bits(uint32_t n, const uint32_t* d_bits, uint32_t one_bits, uint32_t zero_bits, void* d_out, void* stream);
 /* number of entries != fill; reference src/cpu/cpu_v_count_mf.hpp:91-107, kernels/count.cl:46. Synchronises. */

@@ -45,6 +45,7 @@ SYMBOLS = [
     "splacu_dist_create", "splacu_dist_destroy", "splacu_dist_info", "splacu_dcsr_create", "splacu_dcsr_destroy", "splacu_dcsr_bounds",
     "splacu_dist_mxv_masked", "splacu_dist_vxm_masked_begin", "splacu_dist_vxm_masked_emit",
     "splacu_v_eadd_dense_op", "splacu_v_eadd_fdb_dense_op", "splacu_v_eadd_fdb_sparse_begin_op", "splacu_jit_compile", "splacu_jit_compile_count",
+    "splacu_csr_hub_cols", "splacu_mxv_masked_part", "splacu_v_gather", "splacu_v_scatter",
 ]
 
 
@@ -126,6 +127,8 @@ def load_library(build_if_missing=True):
         "splacu_dist_mxv_masked": [vp, i32, i32, i32, i32, vp, vp, vp, u32, i32, vp],
         "splacu_dist_vxm_masked_begin": [vp, i32, i32, i32, i32, u32, vp, vp, vp, pu32, vp], "splacu_dist_vxm_masked_emit": [vp, vp, vp, vp],
         "splacu_jit_compile": [i32, pop, pop, pop, C.POINTER(C.c_size_t)], "splacu_jit_compile_count": [C.POINTER(C.c_uint64)],
+        "splacu_csr_hub_cols": [vp, pu32, C.POINTER(vp)], "splacu_mxv_masked_part": [vp, i32, i32, i32, i32, vp, vp, vp, vp, u32, i32, vp],
+        "splacu_v_gather": [u32, vp, vp, vp, vp], "splacu_v_scatter": [u32, vp, vp, vp, u32, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -327,6 +330,31 @@ class Backend:
         self._check(self.lib.splacu_mxv_masked(M.handle, code, BIN[op_mult], BIN[op_add], SEL[op_select], _ptr(v), _ptr(mask),
                                                _ptr(out), scalar_bits(code, init), int(bool(early_exit)), self.stream_ptr))
         return out
+
+    def mxv_masked_part(self, M, part, v, hub_vals, mask, op_mult, op_add, op_select, init, out, stream_ptr=None):
+        """One part of the two-part pull product (splacu_mxv_masked_part): part 1 = mask pass + hub classes (reads hub_vals, or v when
+        hub_vals is None), part 2 = everything that reads v + the fix-ups."""
+        self._check(self.lib.splacu_mxv_masked_part(M.handle, M.dtype, BIN[op_mult], BIN[op_add], SEL[op_select], _ptr(v), _ptr(hub_vals), _ptr(mask),
+                                                    _ptr(out), scalar_bits(M.dtype, init), int(part), stream_ptr if stream_ptr is not None else self.stream_ptr))
+        return out
+
+    def csr_hub_cols(self, M):
+        """the hub columns of the handle (device tensor of column ids in slot order; empty when the matrix has no column classes)"""
+        n, ptr = C.c_uint32(0), C.c_void_p(0)
+        self._check(self.lib.splacu_csr_hub_cols(M.handle, C.byref(n), C.byref(ptr)))
+        out = torch.empty(n.value, dtype=torch.int32, device=self.device)
+        if n.value:
+            self._check(self.lib.splacu_memcpy_d2d(_ptr(out), ptr, n.value * 4, self.stream_ptr))
+            self.sync()
+        return out
+
+    def v_gather(self, idx, src, dst, stream_ptr=None):
+        self._check(self.lib.splacu_v_gather(idx.numel(), _ptr(idx), _ptr(src), _ptr(dst), stream_ptr if stream_ptr is not None else self.stream_ptr))
+        return dst
+
+    def v_scatter(self, idx, src, dst, stream_ptr=None):
+        self._check(self.lib.splacu_v_scatter(idx.numel(), _ptr(idx), _ptr(src), _ptr(dst), dst.numel(), stream_ptr if stream_ptr is not None else self.stream_ptr))
+        return dst
 
     def vxm_masked(self, M, vi, vx, mask, op_mult, op_add, op_select, out=None):
         """r = v x M (push) over the sparse vector (vi, vx). Mirrors exec_vxm_masked(r, mask, v, M, ...).

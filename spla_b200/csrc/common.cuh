@@ -124,8 +124,10 @@ namespace splacu {
     void scat_free(Csr* M);
     int  scat_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, void* d_r, const uint32_t* gate,
                   uint32_t gate_min, cudaStream_t s);
+    // parts: bit 0 = the hub classes (they read only the packed hub values), bit 1 = everything that reads v itself (row classes, tail
+    // classes) + the fix-ups, bit 2 = the prologue (r = init when no mask pass has filled it); 7 = the whole product
     int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r,
-                uint32_t init_bits, const uint32_t* gate, uint32_t gate_min, cudaStream_t s);
+                uint32_t init_bits, const uint32_t* gate, uint32_t gate_min, cudaStream_t s, int parts = 7);
 
     struct Csr {
         uint32_t        n_rows = 0, n_cols = 0, nnz = 0;

@@ -1114,11 +1114,20 @@ namespace splacu {
     }
 
     template<typename T, typename S>
-    static int launch_tiles(S sr, Select sel, const Csr* M, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
+    // parts: 4 = prologue (r = init / the mask pass), 1 = hub classes, 2 = everything that reads v + the fix-ups; 7 = the whole product
+    static int launch_tiles(S sr, Select sel, const Csr* M, const T* v, const T* mask, T* r, T init, cudaStream_t s, int parts = 7,
+                            const void* d_hub_vals = nullptr) {
         int rc;
+        const bool classes = M->n_phases && M->phase[0].seg;
+        if (parts != 7 && !classes) {// no column classes: nothing can start before v is complete, the last part is the whole product
+            if (!(parts & 2)) return 0;
+            parts = 7;
+        }
         if (get_option(OPT_MXV_L2_PERSIST) && (size_t) M->nnz * 8 > (size_t) 64 << 20)
             if ((rc = set_persisting_window(v, (size_t) M->n_cols * 4, s))) return rc;
-        if (M->n_hub) {
+        if (M->n_hub && (parts & 1) && d_hub_vals) {// the caller brings the hub values (gathered from their owners)
+            SPLACU_CUDA(cudaMemcpyAsync(M->hub_vals, d_hub_vals, (size_t) M->n_hub * 4, cudaMemcpyDeviceToDevice, s));
+        } else if (M->n_hub && (parts & 1)) {
             SPLACU_PROFILE("splacu/mxv/hub_pack", s);
             mxv_hub_pack_kernel<<<(M->n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->hub_cols, M->n_hub, reinterpret_cast<const uint32_t*>(v), M->hub_vals);
             SPLACU_LAUNCH_CHECK();
@@ -1131,13 +1140,15 @@ namespace splacu {
             if (sel.reads_mask && M->sel_count) {
                 gate     = M->sel_count;
                 gate_min = (uint32_t) ((uint64_t) M->n_rows * (uint64_t) get_option(OPT_MXV_SEG_MIN_DENSITY) / 100u);
+            }
+            if (gate && (parts & 4)) {
                 SPLACU_PROFILE("splacu/mxv/mask_count_fill", s);
                 SPLACU_CUDA(cudaMemsetAsync(M->sel_count, 0, 4, s));
                 mask_count_fill_kernel<T><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count, M->sel_bits, r, init);
                 SPLACU_LAUNCH_CHECK();
             }
-            rc = seg_mxv(M, TypeCode<T>::value, sr.mult_op(), sr.add_op(), sel, v, mask, r, to_bits(init), gate, gate_min, s);
-            if (rc || !gate) return rc;
+            rc = seg_mxv(M, TypeCode<T>::value, sr.mult_op(), sr.add_op(), sel, v, mask, r, to_bits(init), gate, gate_min, s, parts);
+            if (rc || !gate || !(parts & 2)) return rc;
             SPLACU_PROFILE("splacu/mxv/csr_pass_gated", s);
             const TileJob job = {M->Ap, M->Aj, M->Ax, M->nnz, M->n_tiles, M->tile_rows, M->carry, (int) M->vec_ok, nullptr, 0u, 0, gate, gate_min};
             return launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, s);
@@ -1167,6 +1178,44 @@ namespace splacu {
 }// namespace splacu
 
 using namespace splacu;
+
+extern "C" int splacu_csr_hub_cols(splacu_csr handle, uint32_t* n_hub, const uint32_t** d_cols) {
+    SPLACU_REQUIRE(handle, "null matrix handle");
+    const Csr* M = reinterpret_cast<const Csr*>(handle);
+    const bool classes = M->n_phases && M->phase[0].seg;
+    if (n_hub) *n_hub = classes ? M->n_hub : 0u;
+    if (d_cols) *d_cols = classes ? M->hub_cols : nullptr;
+    return SPLACU_OK;
+}
+
+extern "C" int splacu_mxv_masked_part(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select, const void* d_v, const void* d_hub_vals,
+                                      const void* d_mask, void* d_r, uint32_t init_bits, int part, void* stream) {
+    SPLACU_CHECK_INIT();
+    SPLACU_PROFILE((part & 2) ? "splacu/mxv_masked_part2" : ((part & 1) ? "splacu/mxv_masked_part1" : "splacu/mxv_masked_part0"), resolve_stream(stream));
+    SPLACU_REQUIRE(handle, "null matrix handle");
+    SPLACU_REQUIRE(part == SPLACU_PART_PROLOGUE || part == SPLACU_PART_HUB || part == (SPLACU_PART_PROLOGUE | SPLACU_PART_HUB) || part == SPLACU_PART_REST,
+                   "part must be PROLOGUE, HUB, PROLOGUE | HUB or REST");
+    const Csr* M = reinterpret_cast<const Csr*>(handle);
+    SPLACU_REQUIRE(op_valid_for(dtype, op_mult), "op_mult not defined for dtype");
+    SPLACU_REQUIRE(op_valid_for(dtype, op_add), "op_add not defined for dtype");
+    SPLACU_REQUIRE(is_assoc_commutative(op_add), "the two-part product needs an associative + commutative op_add");
+    SPLACU_REQUIRE(op_select >= 0 && op_select < SPLACU_SELOP_COUNT, "unknown op_select");
+    if (M->n_rows == 0) return SPLACU_OK;
+    const Select sel = make_select(op_select);
+    SPLACU_REQUIRE(d_r, "null result pointer");
+    SPLACU_REQUIRE(d_mask || !sel.reads_mask, "null mask pointer");
+    SPLACU_REQUIRE((part & 2) ? (d_v || M->nnz == 0) : (!(part & 1) || d_hub_vals || d_v || M->n_hub == 0), "null vector pointer");
+    cudaStream_t s = resolve_stream(stream);
+    if (M->nnz == 0 || (!sel.reads_mask && sel.classes == 0u)) return (part & 2) ? splacu_fill(d_r, init_bits, M->n_rows, stream) : SPLACU_OK;
+    return dispatch_dtype(dtype, [&](auto tag) {
+        using T = decltype(tag);
+        return dispatch_semiring<T>(op_mult, op_add, [&](auto sr) {
+            using S = decltype(sr);
+            return launch_tiles<T, S>(sr, sel, M, static_cast<const T*>(d_v), static_cast<const T*>(d_mask), static_cast<T*>(d_r), from_bits<T>(init_bits), s,
+                                      part, d_hub_vals);
+        });
+    });
+}
 
 extern "C" int splacu_mxv_masked(splacu_csr handle, int dtype, int op_mult, int op_add, int op_select,
                                  const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits, int early_exit, void* stream) {

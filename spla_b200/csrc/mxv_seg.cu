@@ -371,6 +371,8 @@ namespace splacu {
         }
     }
 
+    static thread_local bool g_split_call = false;// splacu_mxv_masked_part: the merged fix-up closes the second part
+
     // The fix-ups of ALL classes in one cooperative launch: class by class with a grid barrier in between, so that the additions onto a
     // row that spans tiles in several classes keep their fixed order (class passes first, then the chains in class order). One launch
     // and n - 1 grid barriers instead of n dependent launches of ~10 us each between the class passes (in the stream: 60 us of a
@@ -495,7 +497,7 @@ namespace splacu {
                                                     ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
             SPLACU_LAUNCH_CHECK();
         }
-        if (!get_option(OPT_MXV_FIXUP_MERGE)) {
+        if (!get_option(OPT_MXV_FIXUP_MERGE) && !g_split_call) {
             SPLACU_PROFILE(kLabels[1][p], s);
             mxv_seg_fixup_kernel<T, S><<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sel, ph.chain, ph.chain_row, ph.head, ph.tail, sel_bits, r,
                                                                                             ph.n_tiles, gate, gate_min);
@@ -505,10 +507,10 @@ namespace splacu {
     }
 
     int seg_mxv(const Csr* M, int dtype, int op_mult, int op_add, const Select& sel, const void* d_v, const void* d_mask, void* d_r, uint32_t init_bits,
-                const uint32_t* gate, uint32_t gate_min, cudaStream_t s) {
+                const uint32_t* gate, uint32_t gate_min, cudaStream_t s, int parts) {
         // every class accumulates onto r, which starts as init everywhere (unselected and empty rows keep it); with a gate the
         // caller's mask-count pass has filled it already
-        if (!gate) {
+        if (!gate && (parts & 4)) {
             const int rc = splacu_fill(d_r, init_bits, M->n_rows, s);
             if (rc) return rc;
         }
@@ -517,9 +519,10 @@ namespace splacu {
             return SPLACU_E_INVALID;
         }
         (void) d_mask;
+        g_split_call   = (parts & 3) != 3;
         const int only = (int) get_option(OPT_MXV_PHASE_ONLY);
         // the row classes of the tail first (mxv_scat.cu): their merge kernels are long done when the tail class needs the SMs
-        if (!only || only > M->n_phases) {
+        if ((parts & 2) && (!only || only > M->n_phases)) {
             const int rc = scat_mxv(M, dtype, op_mult, op_add, sel, d_v, d_r, gate, gate_min, s);
             if (rc) return rc;
         }
@@ -534,12 +537,14 @@ namespace splacu {
                     const CsrPhase& ph = M->phase[p];
                     if (ph.nnz == 0 || (only && only != p + 1)) continue;
                     ran[n_ran++] = p;
+                    if (!(parts & (ph.idx16 ? 1 : 2))) continue;
                     int e;
                     if (sel.reads_mask && gate) e = ph.idx16 ? launch_seg<T, S, true, true>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s) : launch_seg<T, S, true, false>(sr, sel, M, ph, v, M->sel_bits, r, gate, gate_min, s);
                     else e = ph.idx16 ? launch_seg<T, S, false, true>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s) : launch_seg<T, S, false, false>(sr, sel, M, ph, v, nullptr, r, nullptr, 0u, s);
                     if (e) return e;
                 }
-                if (get_option(OPT_MXV_FIXUP_MERGE))
+                if (!(parts & 2)) return 0;// the fix-ups close the product: with the part that runs last
+                if (get_option(OPT_MXV_FIXUP_MERGE) || (parts & 3) != 3)
                     return launch_fixup_all<T, S>(sr, M, ran, n_ran, (sel.reads_mask && gate) ? M->sel_bits : nullptr, r, gate, gate_min, s);
                 return 0;
             });

@@ -230,6 +230,12 @@ namespace splacu {
         }
     }
 
+    __global__ void __launch_bounds__(kBlock) gather_kernel(uint32_t n, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ src,
+                                                            uint32_t* __restrict__ dst) {
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) dst[k] = src[idx[k]];
+    }
+
     // dense -> bitmap of entries != fill (value comparison in T). One warp ballot = one bitmap word.
     template<typename T>
     __global__ void __launch_bounds__(kBlock) mark_nonfill_kernel(const T* __restrict__ dense, uint32_t n, T fill, uint32_t* __restrict__ bitmap) {
@@ -461,6 +467,26 @@ int splacu_coo_to_dense(uint32_t n, uint32_t fill_bits, uint32_t nv, const uint3
     SPLACU_REQUIRE(d_vi && d_vx, "null coo pointers");
     cudaStream_t s = resolve_stream(stream);
     scatter_kernel<<<grid_for(nv, kBlock, 8), kBlock, 0, s>>>(nv, d_vi, static_cast<const uint32_t*>(d_vx), static_cast<uint32_t*>(d_dense), n);
+    SPLACU_LAUNCH_CHECK();
+    return SPLACU_OK;
+}
+
+int splacu_v_gather(uint32_t n, const uint32_t* d_idx, const void* d_src, void* d_dst, void* stream) {
+    SPLACU_CHECK_INIT();
+    if (n == 0) return SPLACU_OK;
+    SPLACU_REQUIRE(d_idx && d_src && d_dst, "null pointer");
+    cudaStream_t s = resolve_stream(stream);
+    gather_kernel<<<grid_for(n, kBlock, 8), kBlock, 0, s>>>(n, d_idx, static_cast<const uint32_t*>(d_src), static_cast<uint32_t*>(d_dst));
+    SPLACU_LAUNCH_CHECK();
+    return SPLACU_OK;
+}
+
+int splacu_v_scatter(uint32_t n, const uint32_t* d_idx, const void* d_src, void* d_dst, uint32_t n_dst, void* stream) {
+    SPLACU_CHECK_INIT();
+    if (n == 0) return SPLACU_OK;
+    SPLACU_REQUIRE(d_idx && d_src && d_dst, "null pointer");
+    cudaStream_t s = resolve_stream(stream);
+    scatter_kernel<<<grid_for(n, kBlock, 8), kBlock, 0, s>>>(n, d_idx, static_cast<const uint32_t*>(d_src), static_cast<uint32_t*>(d_dst), n_dst);
     SPLACU_LAUNCH_CHECK();
     return SPLACU_OK;
 }

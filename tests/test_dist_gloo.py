@@ -227,3 +227,43 @@ def _bfs_worker(rank, world, port, out_dir):
 def test_bfs_dist_matches_sequential_bfs(tmp_path, world):
     mp.spawn(_bfs_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"bfs_ok{r}").exists() for r in range(world))
+
+
+def _hub_plan_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from spla_b200 import dist as sd
+
+        w = 96  # equal windows of the padded layout
+        g = torch.Generator().manual_seed(11)
+        v_full = torch.randint(-1000, 1000, (world * w,), generator=g, dtype=torch.int32)  # the same on every rank
+        gr = torch.Generator().manual_seed(100 + rank)
+        # every rank has its OWN hub list (its handle ranks the columns of its row block): a random subset, random slot order,
+        # with owners that get nothing from this rank and, on rank 1, an empty window request to rank 0's last element
+        n_hub = [40, 57, 13][rank % 3]
+        hub_cols = torch.randperm(world * w, generator=gr)[:n_hub].to(torch.int32)
+        if rank == 1:
+            hub_cols = hub_cols[hub_cols >= w]  # nothing from owner 0
+        plan = sd.hub_exchange_plan(hub_cols, w)
+        assert sum(plan["recv_counts"]) == hub_cols.numel() and len(plan["recv_counts"]) == world
+        assert plan["req"].numel() == sum(plan["send_counts"])
+        window = v_full[rank * w:(rank + 1) * w]
+        send = window[plan["req"].long()].contiguous()  # what splacu_v_gather does on the device
+        recv = torch.empty(hub_cols.numel(), dtype=torch.int32)
+        dist.all_to_all_single(recv, send, output_split_sizes=plan["recv_counts"], input_split_sizes=plan["send_counts"])
+        hub_vals = torch.full((hub_cols.numel(),), -7, dtype=torch.int32)
+        hub_vals[plan["order"]] = recv  # splacu_v_scatter
+        assert torch.equal(hub_vals, v_full[hub_cols.long()]), "hub values gathered from their owners differ from v[hub_cols]"
+        open(os.path.join(out_dir, f"hub_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_hub_value_exchange_plan(tmp_path, world):
+    """The owner-side gather / all-to-all / slot scatter that feeds part 1 of the two-part pull product (dist.PipelinedPull) delivers
+    exactly v[hub_cols] to every rank, for uneven per-rank hub lists and owners that contribute nothing."""
+    mp.spawn(_hub_plan_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"hub_ok{r}")) for r in range(world))

@@ -740,3 +740,67 @@ def test_pull_row_classes_forced(backend, oracle, dtype, om, oa, osel, slots, co
         backend.sync()
         assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"row classes mxv rep {rep}",
                       bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,om,oa,osel", [(INT, "MULT", "PLUS", "EQZERO"), (FLOAT, "MULT", "PLUS", "ALWAYS"), (FLOAT, "PLUS", "MIN", "NQZERO"),
+                                               (UINT, "BAND", "BOR", "NQZERO"), (FLOAT, "MULT", "PLUS", "NQZERO")])
+@pytest.mark.parametrize("slots,col_phases,row_classes,given", [(16, 2, 1, True), (64, 3, 0, False), (1024, 1, 1, True), (45056, 4, 1, True)])
+def test_pull_two_part_product(backend, oracle, dtype, om, oa, osel, slots, col_phases, row_classes, given):
+    """splacu_mxv_masked_part: prologue + hub classes (fed with v[hub_cols] gathered by the caller or with v itself) followed by
+    the rest (row classes, tail classes, fix-ups, gated CSR pass) equals the one-call product -- what the overlapped multi-GPU step relies
+    on. Forced classes on a small skewed matrix; the last parameter set has no classes (part 1 is a no-op, part 2 the whole product)."""
+    rng = np.random.default_rng(zlib.crc32(repr(("2part", dtype, om, oa, slots)).encode()))
+    n_rows, n_cols = 2900, 3000
+    kind = "positive" if (om, oa) == ("PLUS", "MIN") else ("unit" if dtype == FLOAT else "small")
+    Ap, Aj, Ax = _skewed_csr(rng, dtype, n_rows, n_cols, kind)
+    try:
+        if slots < 45056:
+            backend.set_option("mxv_hub", 3)
+        backend.set_option("mxv_phase_slots", slots)
+        backend.set_option("mxv_phases", col_phases)
+        backend.set_option("mxv_hub_min_count", 1)
+        backend.set_option("mxv_row_classes", row_classes)
+        backend.set_option("mxv_row_min_count", 4)
+        backend.set_option("mxv_row_min_nnz", 0)
+        M = make_csr(backend, n_rows, n_cols, Ap, Aj, Ax)
+    finally:
+        backend.set_option("mxv_hub", 1)
+        backend.set_option("mxv_phase_slots", 45056)
+        backend.set_option("mxv_phases", 4)
+        backend.set_option("mxv_hub_min_count", 16)
+        backend.set_option("mxv_row_classes", 1)
+        backend.set_option("mxv_row_min_count", 64)
+        backend.set_option("mxv_row_min_nnz", 25165824)
+    hub_cols = backend.csr_hub_cols(M)
+    assert (hub_cols.numel() > 0) == (slots < 45056)
+    for rep in range(3):
+        v = cases.rand_values(rng, dtype, n_cols, kind)
+        mask = cases.rand_values(rng, dtype, n_rows)
+        if rep == 2:
+            mask[rng.random(n_rows) < 0.8] = 0  # sparse selection: the gated CSR pass of part 2 does the work
+        init = np.float32(3.0e38) if (om, oa) == ("PLUS", "MIN") else (0 if rep == 0 else 3)
+        want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
+        dv, dm = to_dev(v, backend), to_dev(mask, backend)
+        out = backend.empty(n_rows, like=dv)
+        hub_vals = None
+        if given and hub_cols.numel():
+            hub_vals = backend.empty(hub_cols.numel(), like=dv)
+            backend.v_gather(hub_cols, dv, hub_vals)
+            # the scatter is the inverse on a permutation
+            perm = torch.randperm(hub_cols.numel(), device=backend.device).to(torch.int32)
+            tmp = backend.empty(hub_cols.numel(), like=dv)
+            backend.v_gather(perm, hub_vals, tmp)
+            back = backend.empty(hub_cols.numel(), like=dv)
+            backend.v_scatter(perm, tmp, back)
+            backend.sync()
+            assert torch.equal(back.view(torch.int32), hub_vals.view(torch.int32))
+        if rep == 1:  # prologue on its own, then the hub classes
+            backend.mxv_masked_part(M, 4, None, None, dm, om, oa, osel, init, out)
+            backend.mxv_masked_part(M, 1, dv if hub_vals is None else None, hub_vals, dm, om, oa, osel, init, out)
+        else:
+            backend.mxv_masked_part(M, 4 | 1, dv if hub_vals is None else None, hub_vals, dm, om, oa, osel, init, out)
+        backend.mxv_masked_part(M, 2, dv, None, dm, om, oa, osel, init, out)
+        backend.sync()
+        assert_values(to_np(out, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"two-part mxv rep {rep}",
+                      bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
