@@ -90,6 +90,78 @@ namespace splacu {
             chain[t]     = w;
             chain_row[t] = row;
         }
+        // Build-time reordering of a hub class against shared-memory bank conflicts. The kernel's 16 table gathers of a tile are 16 warp
+        // instructions: step i reads the i-th entry of every lane, 32 random slots of a 45 K-word table -> ~3.4 wavefronts per
+        // instruction instead of 1 (the largest share of the LSU pipe's work in a hub pass). The ORDER of a row's entries is free (the add
+        // is associative + commutative, and the fold order is fixed either way), so inside every lane the entries of one row run are
+        // permuted such that at each step the lanes hit banks that are as distinct as possible: steps in order, lanes in order, each lane
+        // takes from the rest of its current run the entry whose bank is least loaded at this step. One warp per tile, lane-serial
+        // (512 decisions per tile, once per matrix). Flags, segment lists and chains are untouched (run lengths do not change).
+        __global__ void __launch_bounds__(kBlock) seg_bank_order_kernel(uint32_t* __restrict__ idx, uint32_t* __restrict__ vals, const uint32_t* __restrict__ flags,
+                                                                        uint32_t n_tiles) {
+            __shared__ uint16_t s_slot[kBlock / 32][32][17];// [warp][lane][entry] (+1: no bank conflicts on the lane-serial walk)
+            __shared__ uint32_t s_val[kBlock / 32][32][17];
+            __shared__ uint8_t  s_load[kBlock / 32][32];
+            const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+            const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+            for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += n_warps) {
+                uint4*         i4 = reinterpret_cast<uint4*>(idx) + (size_t) t * 64;
+                uint4*         v4 = reinterpret_cast<uint4*>(vals) + (size_t) t * 128;
+                const uint32_t fl = (flags[t * 16u + (lane >> 1)] >> ((lane & 1u) * 16u)) & 0xffffu;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint4    x    = i4[h * 32 + lane];
+                    const uint32_t q[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        s_slot[w][lane][8 * h + 2 * k]     = (uint16_t) (q[k] & 0xffffu);
+                        s_slot[w][lane][8 * h + 2 * k + 1] = (uint16_t) (q[k] >> 16);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 x = v4[g * 32 + lane];
+                    s_val[w][lane][4 * g + 0] = x.x, s_val[w][lane][4 * g + 1] = x.y, s_val[w][lane][4 * g + 2] = x.z, s_val[w][lane][4 * g + 3] = x.w;
+                }
+                __syncwarp();
+                for (int i = 0; i < 16; ++i) {
+                    s_load[w][lane] = 0;
+                    __syncwarp();
+                    // end of the run that holds position i: the first flagged position >= i (15 when the lane's tail stays open)
+                    const uint32_t rest = fl >> i;
+                    const int      end  = rest ? i + __ffs(rest) - 1 : 15;
+                    for (uint32_t L = 0; L < 32; ++L) {
+                        if (lane == L) {
+                            int      best = i;
+                            uint32_t bl   = s_load[w][s_slot[w][lane][i] & 31u];
+                            for (int c = i + 1; c <= end && bl; ++c) {
+                                const uint32_t l = s_load[w][s_slot[w][lane][c] & 31u];
+                                if (l < bl) bl = l, best = c;
+                            }
+                            if (best != i) {
+                                const uint16_t a = s_slot[w][lane][i];
+                                const uint32_t b = s_val[w][lane][i];
+                                s_slot[w][lane][i] = s_slot[w][lane][best], s_val[w][lane][i] = s_val[w][lane][best];
+                                s_slot[w][lane][best] = a, s_val[w][lane][best] = b;
+                            }
+                            s_load[w][s_slot[w][lane][i] & 31u] = (uint8_t) (bl + 1u);
+                        }
+                        __syncwarp();
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t q[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) q[k] = (uint32_t) s_slot[w][lane][8 * h + 2 * k] | ((uint32_t) s_slot[w][lane][8 * h + 2 * k + 1] << 16);
+                    i4[h * 32 + lane] = make_uint4(q[0], q[1], q[2], q[3]);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    v4[g * 32 + lane] = make_uint4(s_val[w][lane][4 * g + 0], s_val[w][lane][4 * g + 1], s_val[w][lane][4 * g + 2], s_val[w][lane][4 * g + 3]);
+                __syncwarp();
+            }
+        }
     }// namespace
 
     // flags / seg_base / segment list of a lane-blocked tile array from the extents of its units (rows of a column class, columns
@@ -149,6 +221,10 @@ namespace splacu {
             SEG_CUDA(cudaMalloc(&ph.tail, (size_t) nt * 4));
             seg_chain_kernel<<<(nt + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.Ap, ph.flags, ph.seg_base, ph.seg_row, nt, ph.chain, ph.chain_row);
             count_launch(1);
+            if (ph.idx16 && get_option(OPT_MXV_BANK_ORDER)) {
+                seg_bank_order_kernel<<<grid_for((size_t) nt * 32, kBlock, 8), kBlock, 0, s>>>(reinterpret_cast<uint32_t*>(ph.Aj), ph.Ax, ph.flags, nt);
+                count_launch(1);
+            }
             SEG_CUDA(cudaStreamSynchronize(s));
             SEG_CUDA(cudaGetLastError());
             ph.seg = true;
@@ -462,6 +538,77 @@ namespace splacu {
         return 0;
     }
 
+    // The same fix-ups WITHOUT an order between the classes: one plain launch over the tiles of all classes, the chain sums go onto r
+    // with atomics (red.global for PLUS / MIN / MAX / bitwise, CAS for MULT). No grid barriers (fixup_all: 43 us in the stream, most of
+    // it barrier and dependent-load latency of five small passes in a row). Integer, MIN / MAX, logical and bitwise results do not
+    // depend on the order; a FLOAT PLUS / MULT row that spans tiles in several classes receives its (at most n) chain sums in arrival
+    // order, i.e. reproducible up to the rounding of those few additions -- as the row classes of the tail already are. Option
+    // mxv_fixup_merge = 2 (default); 1 keeps the ordered cooperative launch.
+    // LOR / LAND normalise their result to 0 / 1 even when the other operand is the identity (add(init, 0) != init for init = 5), which
+    // the skip-if-no-change atomics of atomic_combine do not reproduce on a raw init value: those adds keep the ordered launch
+    template<typename T> static bool atomic_fixup_ok(int op_add) { return op_add != SPLACU_LOR && op_add != SPLACU_LAND; }
+    template<typename T, typename S>
+    __global__ void __launch_bounds__(kBlock) mxv_seg_fixup_flat_kernel(S sr, FixAll a, const uint32_t* __restrict__ sel_bits, T* r,
+                                                                        const uint32_t* __restrict__ gate, uint32_t gate_min) {
+        if (gate && *gate < gate_min) return;
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t       t    = blockIdx.x * blockDim.x + threadIdx.x;// position in the concatenation of the classes, each padded to whole warps
+        int            p    = 0;
+        for (; p < a.n; ++p) {
+            const uint32_t padded = (a.c[p].n_tiles + 31u) & ~31u;
+            if (t < padded) break;
+            t -= padded;
+        }
+        if (p == a.n) return;// whole warps leave together (the classes are padded to warps)
+        const uint32_t* __restrict__ chain     = a.c[p].chain;
+        const uint32_t* __restrict__ chain_row = a.c[p].chain_row;
+        const uint32_t* __restrict__ head      = a.c[p].head;
+        const uint32_t* __restrict__ tail      = a.c[p].tail;
+        uint32_t len = 0, row = 0;
+        if (t < a.c[p].n_tiles) {
+            len = chain[t] & 0x7fffffffu;
+            if (len) {
+                row = chain_row[t];
+                if (sel_bits && !((sel_bits[row >> 5] >> (row & 31u)) & 1u)) len = 0;
+            }
+        }
+        if (len > 0 && len <= 4) {
+            T acc = from_bits<T>(tail[t - len]);
+            for (uint32_t u = t - len + 1; u < t; ++u) acc = sr.add(acc, from_bits<T>(tail[u]));
+            acc = sr.add(acc, from_bits<T>(head[t]));
+            atomic_combine<T>(sr.add_op(), r + row, acc, sr.identity());
+        }
+        uint32_t long_mask = __ballot_sync(0xffffffffu, len > 4);
+        while (long_mask) {
+            const int src = __ffs(long_mask) - 1;
+            long_mask &= long_mask - 1;
+            const uint32_t t1 = __shfl_sync(0xffffffffu, t, src), L = __shfl_sync(0xffffffffu, len, src);
+            T              acc = sr.identity();
+            for (uint32_t u = lane; u < L; u += 32) acc = sr.add(acc, from_bits<T>(tail[t1 - L + u]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = sr.add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+            if ((int) lane == src) atomic_combine<T>(sr.add_op(), r + row, sr.add(acc, from_bits<T>(head[t])), sr.identity());
+        }
+    }
+    template<typename T, typename S>
+    static int launch_fixup_flat(S sr, const Csr* M, const int* classes, int n, const uint32_t* sel_bits, T* r, const uint32_t* gate, uint32_t gate_min,
+                                 cudaStream_t s) {
+        if (n == 0) return 0;
+        FixAll   a;
+        uint64_t total = 0;
+        a.n = n;
+        for (int i = 0; i < n; ++i) {
+            const CsrPhase& ph = M->phase[classes[i]];
+            a.c[i]             = {ph.chain, ph.chain_row, ph.head, ph.tail, ph.n_tiles};
+            total += (ph.n_tiles + 31u) & ~31u;
+        }
+        if (total == 0) return 0;
+        SPLACU_PROFILE("splacu/mxv/fixup_flat", s);
+        mxv_seg_fixup_flat_kernel<T, S><<<(unsigned) ((total + kBlock - 1) / kBlock), kBlock, 0, s>>>(sr, a, sel_bits, r, gate, gate_min);
+        SPLACU_LAUNCH_CHECK();
+        return 0;
+    }
+
     template<typename T, typename S, bool MASKED, bool IDX16, bool RED = false>
     static int launch_seg(S sr, Select sel, const Csr* M, const CsrPhase& ph, const T* v, const uint32_t* sel_bits, T* r, const uint32_t* gate,
                           uint32_t gate_min, cudaStream_t s) {
@@ -544,6 +691,8 @@ namespace splacu {
                     if (e) return e;
                 }
                 if (!(parts & 2)) return 0;// the fix-ups close the product: with the part that runs last
+                if (get_option(OPT_MXV_FIXUP_MERGE) >= 2 && atomic_fixup_ok<T>(sr.add_op()))
+                    return launch_fixup_flat<T, S>(sr, M, ran, n_ran, (sel.reads_mask && gate) ? M->sel_bits : nullptr, r, gate, gate_min, s);
                 if (get_option(OPT_MXV_FIXUP_MERGE) || (parts & 3) != 3)
                     return launch_fixup_all<T, S>(sr, M, ran, n_ran, (sel.reads_mask && gate) ? M->sel_bits : nullptr, r, gate, gate_min, s);
                 return 0;

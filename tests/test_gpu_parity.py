@@ -230,10 +230,17 @@ def test_pull_column_class_phases_forced(backend, oracle, dtype, om, oa, osel, s
         mask = cases.rand_values(rng, dtype, n_rows)
         init = np.float32(3.0e38) if (om, oa) == ("PLUS", "MIN") else (0 if rep == 0 else 3)
         want = oracle.mxv_masked(dtype, om, oa, osel, Ap, Aj, Ax, v, mask, init, False)
-        got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
-        backend.sync()
-        assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"phases mxv rep {rep}",
-                      bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
+        # the three forms of the fix-up of rows that span tiles: atomics in one plain launch (default), ordered cooperative launch,
+        # one launch per class
+        for fix in (2, 1, 0):
+            try:
+                backend.set_option("mxv_fixup_merge", fix)
+                got = backend.mxv_masked(M, to_dev(v, backend), to_dev(mask, backend), om, oa, osel, init)
+                backend.sync()
+            finally:
+                backend.set_option("mxv_fixup_merge", 2)
+            assert_values(to_np(got, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"phases mxv rep {rep} fix-up {fix}",
+                          bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
     # early exit and non-associative adds keep using the original CSR of the handle
     v = cases.rand_values(rng, dtype, n_cols, kind)
     mask = cases.rand_values(rng, dtype, n_rows)
