@@ -154,6 +154,9 @@ namespace splacu {
         CsrScat   scat[kMaxScat];
         uint32_t* sel_count    = nullptr;// device counter: rows the mask of the current call selects (chooses the masked path on the device)
         uint32_t* sel_bits     = nullptr;// [n_rows / 32] bit i = select(mask[i]) of the current call: what the class passes read
+        // side stream of a product (the gated CSR pass runs beside the class passes), created at first use
+        mutable cudaStream_t side    = nullptr;
+        mutable cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
         // every stored value has the same bit pattern (adjacency matrices): lets the push product run structure-only (vxm_push.cu)
         bool      ax_uniform   = false;
         uint32_t  ax_value     = 0;

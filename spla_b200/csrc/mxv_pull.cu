@@ -477,7 +477,8 @@ namespace splacu {
                     cleanup();
                     return rc;
                 }
-                HUB_CUDA(cudaMalloc(&M->sel_count, 4));
+                HUB_CUDA(cudaMalloc(&M->sel_count, 16));// [0] the count, [1] running total, [2] ticket of the count pass (both return to 0)
+                HUB_CUDA(cudaMemsetAsync(M->sel_count, 0, 16, s));
                 HUB_CUDA(cudaMalloc(&M->sel_bits, ((size_t) M->n_rows + 31) / 32 * 4 + 4));
             } else {
                 HUB_CUDA(cudaMalloc(&M->Aj_hub, (size_t) M->nnz * 4));
@@ -1028,14 +1029,24 @@ namespace splacu {
     // (dense masks) and the CSR kernel that tests the mask before any gather (sparse masks) without a host round trip
     // (the same pass pre-fills r with init for the class passes, which accumulate onto it, and leaves select(mask[i]) as a bitmap:
     //  2 MB that stay in L2 instead of 64 MB read again by every class pass)
+    // The blocks [0, n_main) count / fill; the blocks behind them pack the hub values of v (hub_vals[s] = v[hub_cols[s]]) when the call
+    // is not split -- one launch less in front of the class passes. The counter needs no memset: the blocks add onto out[1], the last
+    // one to finish (ticket out[2]) publishes the total in out[0] and returns out[1] / out[2] to zero.
     template<typename T>
     __global__ void __launch_bounds__(kBlock) mask_count_fill_kernel(Select sel, const T* __restrict__ mask, uint32_t n, uint32_t* __restrict__ out,
-                                                                     uint32_t* __restrict__ sel_bits, T* __restrict__ r, T init) {
+                                                                     uint32_t* __restrict__ sel_bits, T* __restrict__ r, T init, uint32_t n_main,
+                                                                     const uint32_t* __restrict__ hub_cols, uint32_t n_hub, const uint32_t* __restrict__ v,
+                                                                     uint32_t* __restrict__ hub_vals) {
+        if (blockIdx.x >= n_main) {
+            const uint32_t q = (blockIdx.x - n_main) * blockDim.x + threadIdx.x;
+            if (q < n_hub) hub_vals[q] = __ldg(v + hub_cols[q]);
+            return;
+        }
         __shared__ uint32_t s_count;
         if (threadIdx.x == 0) s_count = 0u;
         __syncthreads();
         uint32_t       c      = 0;
-        const uint32_t stride = gridDim.x * blockDim.x;// a multiple of 32: a warp always covers 32 consecutive rows
+        const uint32_t stride = n_main * blockDim.x;// a multiple of 32: a warp always covers 32 consecutive rows
         const uint32_t n_pad  = (n + 31u) & ~31u;
         constexpr int  U      = 4;// independent 32-row groups per warp and step
         for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_pad; i0 += stride * U) {
@@ -1059,7 +1070,15 @@ namespace splacu {
         }
         if ((threadIdx.x & 31u) == 0u && c) atomicAdd(&s_count, c);
         __syncthreads();
-        if (threadIdx.x == 0 && s_count) atomicAdd(out, s_count);
+        if (threadIdx.x == 0) {
+            if (s_count) atomicAdd(out + 1, s_count);
+            __threadfence();
+            if (atomicAdd(out + 2, 1u) == n_main - 1u) {// the last block
+                __threadfence();
+                out[0] = atomicExch(out + 1, 0u);
+                out[2] = 0u;
+            }
+        }
     }
 
     template<typename T, typename S, bool MASKED, int MODE, int WARPS>
@@ -1125,9 +1144,11 @@ namespace splacu {
         }
         if (get_option(OPT_MXV_L2_PERSIST) && (size_t) M->nnz * 8 > (size_t) 64 << 20)
             if ((rc = set_persisting_window(v, (size_t) M->n_cols * 4, s))) return rc;
+        const bool seg_classes = M->n_phases && M->phase[0].seg;
+        const bool fuse_pack   = seg_classes && M->n_hub && parts == 7 && !d_hub_vals && sel.reads_mask && M->sel_count;// packed by the mask pass below
         if (M->n_hub && (parts & 1) && d_hub_vals) {// the caller brings the hub values (gathered from their owners)
             SPLACU_CUDA(cudaMemcpyAsync(M->hub_vals, d_hub_vals, (size_t) M->n_hub * 4, cudaMemcpyDeviceToDevice, s));
-        } else if (M->n_hub && (parts & 1)) {
+        } else if (M->n_hub && (parts & 1) && !fuse_pack) {
             SPLACU_PROFILE("splacu/mxv/hub_pack", s);
             mxv_hub_pack_kernel<<<(M->n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->hub_cols, M->n_hub, reinterpret_cast<const uint32_t*>(v), M->hub_vals);
             SPLACU_LAUNCH_CHECK();
@@ -1143,15 +1164,39 @@ namespace splacu {
             }
             if (gate && (parts & 4)) {
                 SPLACU_PROFILE("splacu/mxv/mask_count_fill", s);
-                SPLACU_CUDA(cudaMemsetAsync(M->sel_count, 0, 4, s));
-                mask_count_fill_kernel<T><<<grid_for(M->n_rows, kBlock, 8), kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count, M->sel_bits, r, init);
+                const uint32_t n_main = (uint32_t) grid_for(M->n_rows, kBlock, 8);
+                const uint32_t n_pack = fuse_pack ? (M->n_hub + kBlock - 1) / kBlock : 0u;
+                mask_count_fill_kernel<T><<<n_main + n_pack, kBlock, 0, s>>>(sel, mask, M->n_rows, M->sel_count, M->sel_bits, r, init, n_main, M->hub_cols,
+                                                                           fuse_pack ? M->n_hub : 0u, reinterpret_cast<const uint32_t*>(v), M->hub_vals);
                 SPLACU_LAUNCH_CHECK();
             }
+            // The mask-first CSR pass of the same call (it returns at once unless the mask is sparse) runs on the handle's SIDE stream,
+            // forked here and joined at the end: for a dense mask its two idle launches (~12 us in a row on the main stream) disappear
+            // behind the class passes; for a sparse mask it is the class passes that return at once.
+            cudaStream_t side = nullptr;
+            if (gate && (parts & 2)) {
+                if (!M->side) {
+                    SPLACU_CUDA(cudaStreamCreateWithFlags(&M->side, cudaStreamNonBlocking));
+                    SPLACU_CUDA(cudaEventCreateWithFlags(&M->ev_fork, cudaEventDisableTiming));
+                    SPLACU_CUDA(cudaEventCreateWithFlags(&M->ev_join, cudaEventDisableTiming));
+                }
+                side = M->side;
+                SPLACU_CUDA(cudaEventRecord(M->ev_fork, s));
+                SPLACU_CUDA(cudaStreamWaitEvent(side, M->ev_fork, 0));
+                {
+                    SPLACU_PROFILE("splacu/mxv/csr_pass_gated", side);
+                    const TileJob job = {M->Ap, M->Aj, M->Ax, M->nnz, M->n_tiles, M->tile_rows, M->carry, (int) M->vec_ok, nullptr, 0u, 0, gate, gate_min};
+                    rc = launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, side);
+                }
+                SPLACU_CUDA(cudaEventRecord(M->ev_join, side));
+                if (rc) {
+                    cudaStreamWaitEvent(s, M->ev_join, 0);
+                    return rc;
+                }
+            }
             rc = seg_mxv(M, TypeCode<T>::value, sr.mult_op(), sr.add_op(), sel, v, mask, r, to_bits(init), gate, gate_min, s, parts);
-            if (rc || !gate || !(parts & 2)) return rc;
-            SPLACU_PROFILE("splacu/mxv/csr_pass_gated", s);
-            const TileJob job = {M->Ap, M->Aj, M->Ax, M->nnz, M->n_tiles, M->tile_rows, M->carry, (int) M->vec_ok, nullptr, 0u, 0, gate, gate_min};
-            return launch_job<T, S, MODE_PLAIN, kWarps>(sr, sel, job, v, mask, r, init, s);
+            if (side) SPLACU_CUDA(cudaStreamWaitEvent(s, M->ev_join, 0));
+            return rc;
         }
         if (M->n_phases) {
             // column classes, hottest first: the hub classes gather from shared memory only, the tail class from v.

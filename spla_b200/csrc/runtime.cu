@@ -397,6 +397,12 @@ int splacu_csr_destroy(splacu_csr handle) {
     if (M->hub_vals) cudaFree(M->hub_vals);
     if (M->Aj_hub) cudaFree(M->Aj_hub);
     if (M->sel_count) cudaFree(M->sel_count);
+    if (M->side) {
+        cudaStreamSynchronize(M->side);
+        cudaStreamDestroy(M->side);
+        cudaEventDestroy(M->ev_fork);
+        cudaEventDestroy(M->ev_join);
+    }
     if (M->sel_bits) cudaFree(M->sel_bits);
     for (int p = 0; p < M->n_phases; ++p) {
         CsrPhase& ph = M->phase[p];

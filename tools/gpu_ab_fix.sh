@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pull or op_pairs or named" 2>&1 | tail -4
-timeout 600 python tools/ab_mxv.py --scale 24 --profile --cfg "mxv_fixup_merge=1" --cfg "mxv_fixup_merge=2" --out gpurun_out/ab_fixup_flat.jsonl 2>&1 | grep -E "fixup|cfg"
-timeout 300 tools/bin/stream_gather_bench 2>&1 | tee gpurun_out/stream_gather_bench.txt
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_configs.py tests/test_gpu_algorithms.py -m gpu -x -q 2>&1 | tail -4
+timeout 600 python tools/ab_mxv.py --scale 24 --profile --cfg "" --out gpurun_out/ab_side.jsonl 2>&1 | tail -14
+timeout 600 python tools/ab_mxv.py --scale 24 --shard 8 --profile --cfg "" 2>&1 | tail -14
