@@ -285,6 +285,9 @@ def main():
     peer = None
     overlap = world > 1 and os.environ.get("SPLA_B200_OVERLAP", "1") == "1" and os.environ.get("SPLA_B200_P2P", "0") != "1"
     pvecs = None
+    reserve = int(os.environ.get("SPLA_B200_RESERVE_SMS", "0"))
+    if reserve:  # SMs the persistent class kernels leave to the kernels of a collective running beside them
+        be.set_option("mxv_reserve_sms", reserve)
     if overlap and os.environ.get("SPLA_B200_OVERLAP_DMA", "1") == "1":
         try:  # peer-mapped vectors: the windows travel on the copy engines
             pvecs = [sd.PeerVector(be, n_vec), sd.PeerVector(be, n_vec)]

@@ -117,6 +117,7 @@ namespace splacu {
     struct Csr;
     // mxv_seg.cu: build the segment metadata of a class from its row extents (ph.Ap) and row counts; run all classes
     int seg_build(const Csr* M, CsrPhase& ph, const uint32_t* d_row_count, cudaStream_t s);
+    int seg_build_fixlist(Csr* M, cudaStream_t s);
     int seg_structure(const uint32_t* d_ext, const uint32_t* d_count, uint32_t n_units, uint32_t n_tiles, uint32_t** flags, uint32_t** seg_base,
                       uint32_t** seg_unit, uint32_t* n_segs, cudaStream_t s);
     // mxv_scat.cu: the row classes of the tail (built from the CSR + the column slot map + the rows chosen by build_phases)
@@ -154,6 +155,10 @@ namespace splacu {
         CsrScat   scat[kMaxScat];
         uint32_t* sel_count    = nullptr;// device counter: rows the mask of the current call selects (chooses the masked path on the device)
         uint32_t* sel_bits     = nullptr;// [n_rows / 32] bit i = select(mask[i]) of the current call: what the class passes read
+        // rows that span tiles in any class: (row << 8 | class) sorted, and the tile the row ends in (the two-launch fix-up, mxv_seg.cu)
+        uint64_t* fix_key      = nullptr;
+        uint32_t* fix_tile     = nullptr;
+        uint32_t  n_fix        = 0;
         // side stream of a product (the gated CSR pass runs beside the class passes), created at first use
         mutable cudaStream_t side    = nullptr;
         mutable cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
@@ -165,8 +170,13 @@ namespace splacu {
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_MXV_RED, OPT_MXV_ROW_CLASSES, OPT_MXV_ROW_MIN_COUNT, OPT_MXV_FIXUP_MERGE, OPT_MXV_ROW_MIN_NNZ, OPT_MXV_BANK_ORDER, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_MXV_RED, OPT_MXV_ROW_CLASSES, OPT_MXV_ROW_MIN_COUNT, OPT_MXV_FIXUP_MERGE, OPT_MXV_ROW_MIN_NNZ, OPT_MXV_BANK_ORDER, OPT_MXV_RESERVE_SMS, OPT_COUNT };
     int64_t get_option(int opt);
+    // CTAs of a persistent one-CTA-per-SM kernel of the pull product: all SMs but the ones option mxv_reserve_sms keeps free
+    inline uint32_t persistent_grid_cap() {
+        const int64_t sms = sm_count(), keep = get_option(OPT_MXV_RESERVE_SMS);
+        return (uint32_t) (keep > 0 && keep < sms ? sms - keep : sms);
+    }
 
     // ---- workspace ------------------------------------------------------------------------
     struct Workspace {

@@ -403,6 +403,7 @@ namespace splacu {
             PH_CUDA(cudaStreamSynchronize(s));
             PH_CUDA(cudaGetLastError());
             if (n_hub_rows && (rc = scat_build(M, d_slot, rows_sorted, n_hub_rows, slots_per_phase, s))) goto done;
+            if (seg && (rc = seg_build_fixlist(M, s))) goto done;
         }
     done:
 #undef PH_CUDA

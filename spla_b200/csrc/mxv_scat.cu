@@ -285,10 +285,12 @@ namespace splacu {
                         return (int) SPLACU_E_INVALID;
                     }
                     SPLACU_PROFILE("splacu/mxv/row_class", s);
-                    kern<<<sc.grid, kScatWarps * 32, smem, s>>>(sr, static_cast<const uint32_t*>(sc.slot), sc.Ax, sc.flags, sc.seg_base, sc.seg_col, v, sc.nnz,
-                                                                sc.n_tiles, sc.n_segs, sc.n_slots, sc.partial, gate, gate_min);
+                    const uint32_t cap  = persistent_grid_cap();
+                    const uint32_t grid = sc.grid < cap ? sc.grid : cap;// the partial tables are sized for sc.grid CTAs
+                    kern<<<grid, kScatWarps * 32, smem, s>>>(sr, static_cast<const uint32_t*>(sc.slot), sc.Ax, sc.flags, sc.seg_base, sc.seg_col, v, sc.nnz,
+                                                             sc.n_tiles, sc.n_segs, sc.n_slots, sc.partial, gate, gate_min);
                     SPLACU_LAUNCH_CHECK();
-                    mxv_scat_merge_kernel<T, S><<<(sc.n_slots + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sc.partial, sc.grid, sc.n_slots, sc.rows, sel_bits, r,
+                    mxv_scat_merge_kernel<T, S><<<(sc.n_slots + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, sc.partial, grid, sc.n_slots, sc.rows, sel_bits, r,
                                                                                                      gate, gate_min);
                     SPLACU_LAUNCH_CHECK();
                 }

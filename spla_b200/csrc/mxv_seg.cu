@@ -22,6 +22,7 @@
 
 #include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -233,6 +234,74 @@ namespace splacu {
         }
     done:
 #undef SEG_CUDA
+        return rc;
+    }
+
+    // ---- the list of rows that span tiles (all classes), for the two-launch fix-up ------------------------
+    namespace {
+        __global__ void __launch_bounds__(kBlock) fix_collect_kernel(const uint32_t* __restrict__ chain, const uint32_t* __restrict__ chain_row, uint32_t n_tiles,
+                                                                     uint32_t cls, uint32_t* __restrict__ counter, uint64_t* __restrict__ keys,
+                                                                     uint32_t* __restrict__ tiles) {
+            const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+            if (t >= n_tiles || !(chain[t] & 0x7fffffffu)) return;
+            const uint32_t pos = atomicAdd(counter, 1u);
+            keys[pos]  = ((uint64_t) chain_row[t] << 8) | cls;// (row, class) is unique: a row ends at most once per class
+            tiles[pos] = t;
+        }
+    }// namespace
+    int seg_build_fixlist(Csr* M, cudaStream_t s) {
+        uint64_t  total = 0;
+        uint32_t *counter = nullptr, *tiles = nullptr;
+        uint64_t* keys  = nullptr;
+        void*     tmp   = nullptr;
+        int       rc    = 0;
+        for (int p = 0; p < M->n_phases; ++p)
+            if (M->phase[p].seg) total += M->phase[p].n_tiles;
+        if (total == 0) return 0;
+#define FX_CUDA(expr)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) {                                              \
+            rc = ::splacu::cuda_fail(_e, #expr, __FILE__, __LINE__);          \
+            goto done;                                                        \
+        }                                                                     \
+    } while (0)
+        {
+            uint32_t n_fix = 0;
+            FX_CUDA(cudaMalloc(&counter, 4));
+            FX_CUDA(cudaMemsetAsync(counter, 0, 4, s));
+            FX_CUDA(cudaMalloc(&keys, total * 8));
+            FX_CUDA(cudaMalloc(&tiles, total * 4));
+            for (int p = 0; p < M->n_phases; ++p) {
+                const CsrPhase& ph = M->phase[p];
+                if (!ph.seg || ph.n_tiles == 0) continue;
+                fix_collect_kernel<<<(ph.n_tiles + kBlock - 1) / kBlock, kBlock, 0, s>>>(ph.chain, ph.chain_row, ph.n_tiles, (uint32_t) p, counter, keys, tiles);
+                count_launch(1);
+            }
+            FX_CUDA(cudaMemcpyAsync(&n_fix, counter, 4, cudaMemcpyDeviceToHost, s));
+            FX_CUDA(cudaStreamSynchronize(s));
+            M->n_fix = n_fix;
+            FX_CUDA(cudaMalloc(&M->fix_key, ((size_t) n_fix + 1) * 8));// allocated even when empty: marks the list as built
+            FX_CUDA(cudaMalloc(&M->fix_tile, ((size_t) n_fix + 1) * 4));
+            if (n_fix) {
+                size_t tmp_bytes = 0;
+                FX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, M->fix_key, tiles, M->fix_tile, (int) n_fix, 0, 40, s));
+                FX_CUDA(cudaMalloc(&tmp, tmp_bytes));
+                FX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, M->fix_key, tiles, M->fix_tile, (int) n_fix, 0, 40, s));
+                FX_CUDA(cudaStreamSynchronize(s));
+            }
+        }
+    done:
+#undef FX_CUDA
+        cudaFree(counter);
+        cudaFree(keys);
+        cudaFree(tiles);
+        cudaFree(tmp);
+        if (rc) {
+            cudaFree(M->fix_key);
+            cudaFree(M->fix_tile);
+            M->fix_key = nullptr, M->fix_tile = nullptr, M->n_fix = 0;
+        }
         return rc;
     }
 
@@ -538,17 +607,17 @@ namespace splacu {
         return 0;
     }
 
-    // The same fix-ups WITHOUT an order between the classes: one plain launch over the tiles of all classes, the chain sums go onto r
-    // with atomics (red.global for PLUS / MIN / MAX / bitwise, CAS for MULT). No grid barriers (fixup_all: 43 us in the stream, most of
-    // it barrier and dependent-load latency of five small passes in a row). Integer, MIN / MAX, logical and bitwise results do not
-    // depend on the order; a FLOAT PLUS / MULT row that spans tiles in several classes receives its (at most n) chain sums in arrival
-    // order, i.e. reproducible up to the rounding of those few additions -- as the row classes of the tail already are. Option
-    // mxv_fixup_merge = 2 (default); 1 keeps the ordered cooperative launch.
-    // LOR / LAND normalise their result to 0 / 1 even when the other operand is the identity (add(init, 0) != init for init = 5), which
-    // the skip-if-no-change atomics of atomic_combine do not reproduce on a raw init value: those adds keep the ordered launch
-    template<typename T> static bool atomic_fixup_ok(int op_add) { return op_add != SPLACU_LOR && op_add != SPLACU_LAND; }
+    // The same fix-ups in TWO plain launches, no grid barriers (fixup_all: 43 us in the stream, most of it barrier and dependent-load
+    // latency of five small passes in a row):
+    //   (1) mxv_seg_chain_sums_kernel, over the tiles of ALL classes at once: the sum of every chain, tail(t0) + ... + tail(t - 1) +
+    //       head(t) left to right, written back into head[t] (only the thread of tile t reads head[t]);
+    //   (2) mxv_seg_fix_rows_kernel, one thread per row that spans tiles in any class: r[row] = add(... add(add(r[row], sum in its
+    //       first class), sum in its next class) ...) in class order, from the list the handle keeps of (row, class, end tile) sorted by
+    //       row and class (built once, seg_build_fixlist).
+    // Same additions in the same order as the ordered cooperative launch: bit-identical results, run-to-run deterministic.
+    // Option mxv_fixup_merge = 2 (default); 1 keeps the cooperative launch, 0 one launch per class.
     template<typename T, typename S>
-    __global__ void __launch_bounds__(kBlock) mxv_seg_fixup_flat_kernel(S sr, FixAll a, const uint32_t* __restrict__ sel_bits, T* r,
+    __global__ void __launch_bounds__(kBlock) mxv_seg_chain_sums_kernel(S sr, FixAll a, const uint32_t* __restrict__ sel_bits,
                                                                         const uint32_t* __restrict__ gate, uint32_t gate_min) {
         if (gate && *gate < gate_min) return;
         const uint32_t lane = threadIdx.x & 31u;
@@ -562,21 +631,20 @@ namespace splacu {
         if (p == a.n) return;// whole warps leave together (the classes are padded to warps)
         const uint32_t* __restrict__ chain     = a.c[p].chain;
         const uint32_t* __restrict__ chain_row = a.c[p].chain_row;
-        const uint32_t* __restrict__ head      = a.c[p].head;
+        uint32_t*                    head      = const_cast<uint32_t*>(a.c[p].head);
         const uint32_t* __restrict__ tail      = a.c[p].tail;
-        uint32_t len = 0, row = 0;
+        uint32_t len = 0;
         if (t < a.c[p].n_tiles) {
             len = chain[t] & 0x7fffffffu;
-            if (len) {
-                row = chain_row[t];
-                if (sel_bits && !((sel_bits[row >> 5] >> (row & 31u)) & 1u)) len = 0;
+            if (len && sel_bits) {
+                const uint32_t row = chain_row[t];
+                if (!((sel_bits[row >> 5] >> (row & 31u)) & 1u)) len = 0;
             }
         }
         if (len > 0 && len <= 4) {
             T acc = from_bits<T>(tail[t - len]);
             for (uint32_t u = t - len + 1; u < t; ++u) acc = sr.add(acc, from_bits<T>(tail[u]));
-            acc = sr.add(acc, from_bits<T>(head[t]));
-            atomic_combine<T>(sr.add_op(), r + row, acc, sr.identity());
+            head[t] = to_bits(sr.add(acc, from_bits<T>(head[t])));
         }
         uint32_t long_mask = __ballot_sync(0xffffffffu, len > 4);
         while (long_mask) {
@@ -587,24 +655,56 @@ namespace splacu {
             for (uint32_t u = lane; u < L; u += 32) acc = sr.add(acc, from_bits<T>(tail[t1 - L + u]));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc = sr.add(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-            if ((int) lane == src) atomic_combine<T>(sr.add_op(), r + row, sr.add(acc, from_bits<T>(head[t])), sr.identity());
+            if ((int) lane == src) head[t] = to_bits(sr.add(acc, from_bits<T>(head[t])));
         }
     }
+    // a.c[] is indexed by CLASS here (n_tiles == 0: the class did not run in this call)
     template<typename T, typename S>
-    static int launch_fixup_flat(S sr, const Csr* M, const int* classes, int n, const uint32_t* sel_bits, T* r, const uint32_t* gate, uint32_t gate_min,
+    __global__ void __launch_bounds__(kBlock) mxv_seg_fix_rows_kernel(S sr, FixAll a, const uint64_t* __restrict__ fix_key, const uint32_t* __restrict__ fix_tile,
+                                                                      uint32_t n_fix, const uint32_t* __restrict__ sel_bits, T* r,
+                                                                      const uint32_t* __restrict__ gate, uint32_t gate_min) {
+        if (gate && *gate < gate_min) return;
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n_fix) return;
+        uint64_t       key = fix_key[i];
+        const uint32_t row = (uint32_t) (key >> 8);
+        if (i > 0 && (uint32_t) (fix_key[i - 1] >> 8) == row) return;// the first entry of a row does the row
+        if (sel_bits && !((sel_bits[row >> 5] >> (row & 31u)) & 1u)) return;
+        T    acc = r[row];
+        bool any = false;
+        for (uint32_t j = i;;) {
+            const uint32_t p = (uint32_t) key & 0xffu;
+            if (a.c[p].n_tiles) {
+                acc = sr.add(acc, from_bits<T>(a.c[p].head[fix_tile[j]]));
+                any = true;
+            }
+            if (++j >= n_fix) break;
+            key = fix_key[j];
+            if ((uint32_t) (key >> 8) != row) break;
+        }
+        if (any) r[row] = acc;
+    }
+    template<typename T, typename S>
+    static int launch_fixup_rows(S sr, const Csr* M, const int* classes, int n, const uint32_t* sel_bits, T* r, const uint32_t* gate, uint32_t gate_min,
                                  cudaStream_t s) {
-        if (n == 0) return 0;
-        FixAll   a;
+        if (n == 0 || M->n_fix == 0) return 0;
+        FixAll   a, by_class;
         uint64_t total = 0;
         a.n = n;
+        by_class.n = kMaxHubPhases + 1;
+        for (int p = 0; p <= kMaxHubPhases; ++p) by_class.c[p] = {nullptr, nullptr, nullptr, nullptr, 0u};
         for (int i = 0; i < n; ++i) {
-            const CsrPhase& ph = M->phase[classes[i]];
-            a.c[i]             = {ph.chain, ph.chain_row, ph.head, ph.tail, ph.n_tiles};
+            const CsrPhase& ph     = M->phase[classes[i]];
+            a.c[i]                 = {ph.chain, ph.chain_row, ph.head, ph.tail, ph.n_tiles};
+            by_class.c[classes[i]] = a.c[i];
             total += (ph.n_tiles + 31u) & ~31u;
         }
         if (total == 0) return 0;
-        SPLACU_PROFILE("splacu/mxv/fixup_flat", s);
-        mxv_seg_fixup_flat_kernel<T, S><<<(unsigned) ((total + kBlock - 1) / kBlock), kBlock, 0, s>>>(sr, a, sel_bits, r, gate, gate_min);
+        SPLACU_PROFILE("splacu/mxv/fixup_rows", s);
+        mxv_seg_chain_sums_kernel<T, S><<<(unsigned) ((total + kBlock - 1) / kBlock), kBlock, 0, s>>>(sr, a, sel_bits, gate, gate_min);
+        SPLACU_LAUNCH_CHECK();
+        mxv_seg_fix_rows_kernel<T, S><<<(M->n_fix + kBlock - 1) / kBlock, kBlock, 0, s>>>(sr, by_class, M->fix_key, M->fix_tile, M->n_fix, sel_bits, r, gate,
+                                                                                         gate_min);
         SPLACU_LAUNCH_CHECK();
         return 0;
     }
@@ -631,7 +731,8 @@ namespace splacu {
             return SPLACU_E_INVALID;
         }
         const uint32_t want = (ph.n_tiles + kW - 1) / kW;
-        const int      grid = (int) (want < (uint32_t) sm_count() ? want : (uint32_t) sm_count());
+        const uint32_t cap  = persistent_grid_cap();
+        const int      grid = (int) (want < cap ? want : cap);
         // per-launch scopes (splacu_profile_enable): the in-stream time of every class pass -- warm caches, no serialisation, which ncu's
         // per-kernel replay does not show (the tail pass: 402 us under ncu, 472 us in the stream)
         static const char* const kLabels[2][kMaxHubPhases + 1] = {
@@ -691,8 +792,8 @@ namespace splacu {
                     if (e) return e;
                 }
                 if (!(parts & 2)) return 0;// the fix-ups close the product: with the part that runs last
-                if (get_option(OPT_MXV_FIXUP_MERGE) >= 2 && atomic_fixup_ok<T>(sr.add_op()))
-                    return launch_fixup_flat<T, S>(sr, M, ran, n_ran, (sel.reads_mask && gate) ? M->sel_bits : nullptr, r, gate, gate_min, s);
+                if (get_option(OPT_MXV_FIXUP_MERGE) >= 2 && M->fix_key)
+                    return launch_fixup_rows<T, S>(sr, M, ran, n_ran, (sel.reads_mask && gate) ? M->sel_bits : nullptr, r, gate, gate_min, s);
                 if (get_option(OPT_MXV_FIXUP_MERGE) || (parts & 3) != 3)
                     return launch_fixup_all<T, S>(sr, M, ran, n_ran, (sel.reads_mask && gate) ? M->sel_bits : nullptr, r, gate, gate_min, s);
                 return 0;

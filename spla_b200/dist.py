@@ -12,6 +12,8 @@ single-device.
 
 The partition helpers are pure index arithmetic on tensors and run on CPU tensors too (used by the gloo tests).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -238,6 +240,10 @@ class PipelinedPull:
         self.hub_vals = torch.empty(n_hub, dtype=torch.float32, device=dev)
         self.comm, self.dma = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         self.comm_ptr, self.dma_ptr = C.c_void_p(self.comm.cuda_stream), C.c_void_p(self.dma.cuda_stream)
+        # further copy streams: the peer copies of one step are spread over them so that several copy engines work at once
+        n_dma = max(1, min(int(os.environ.get("SPLA_B200_DMA_STREAMS", "4")), self.world - 1))
+        self.dma_more = [torch.cuda.Stream(device=dev) for _ in range(n_dma - 1)]
+        self.dma_more_ev = [torch.cuda.Event() for _ in self.dma_more]
         self.ev_done, self.ev_hub, self.ev_full = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.primed, self.k = False, 0
         self.recv_sym = None
@@ -307,10 +313,17 @@ class PipelinedPull:
         # (2) the windows: peer copies on the copy engines, then the barrier of the symmetric allocation
         if pv is not None:
             self.dma.wait_event(self.ev_done)
+            for st in self.dma_more:
+                st.wait_event(self.ev_done)
             off, nbytes = self.w0 * 4, self.w * 4
+            lanes = [self.dma] + self.dma_more
             for d in range(1, self.world):
                 p = (self.rank + d) % self.world
-                be._check(be.lib.splacu_memcpy_d2d(C.c_void_p(pv._ptrs[p] + off), C.c_void_p(dst.data_ptr() + off), nbytes, self.dma_ptr))
+                st = lanes[(d - 1) % len(lanes)]
+                be._check(be.lib.splacu_memcpy_d2d(C.c_void_p(pv._ptrs[p] + off), C.c_void_p(dst.data_ptr() + off), nbytes, C.c_void_p(st.cuda_stream)))
+            for st, ev in zip(self.dma_more, self.dma_more_ev):
+                ev.record(st)
+                self.dma.wait_event(ev)
             with torch.cuda.stream(self.dma):
                 pv.handle.barrier(channel=1)
             self.ev_full.record(self.dma)
