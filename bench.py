@@ -60,7 +60,7 @@ def workload_config(args, n=None, nnz=None, world=1):
         "workload": f"mxv_masked FLOAT {OPS[0]}/{OPS[1]}/{OPS[2]} all-ones mask (PageRank step, E = nnz) on RMAT scale-{args.scale} "
                     f"edge-factor {args.edge_factor}, symmetrised + dedup + no loops, A[i][j] = 0.85/outdeg(i), v = 1/N",
         "graph": f"rmat-{args.scale}",
-        "parallelism": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, vector in the padded equal-window layout, " + ("windows published to the peers by one kernel of NVLink peer stores + device barrier per step" if PEER_MODE[0] else (("hub values exchanged first (small all-to-all), the windows travel as peer copies on the copy engines beside the hub class passes of the next step" if OVERLAP[0] == 2 else "hub values exchanged first (small all-to-all), the in-place ncclAllGather of the windows overlaps the hub class passes of the next step") if OVERLAP[0] else "one in-place ncclAllGather per step")),
+        "parallelism": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, vector in the padded equal-window layout, " + ("windows published to the peers by one kernel of NVLink peer stores + device barrier per step" if PEER_MODE[0] else (("a step starts the exchange of its input (hub values first, then the windows as peer copies on the copy engines into symmetric memory) beside its own mask pass and hub class passes; one CUDA graph per direction of the ping-pong" if OVERLAP[0] == 2 else "hub values exchanged first (small all-to-all), the in-place ncclAllGather of the windows overlaps the hub class passes of the next step") if OVERLAP[0] else "one in-place ncclAllGather per step")),
         "cache": "inputs larger than L2 (CSR >> 126 MB), no flush between iterations",
     }
     if n is not None:
@@ -364,8 +364,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    GRAPHS = False
     with torch.cuda.stream(be.stream):
         a, b = v, v_next
+        if pp and pvecs:
+            GRAPHS = pp.prepare(a, b)  # both directions of the ping-pong as CUDA graphs (one host call per step)
+            a.fill_(1.0 / n)
+            b.fill_(1.0 / n)
         for _ in range(max(3, args.warmup)):
             step(a, b)
             a, b = b, a
@@ -375,17 +380,19 @@ def main():
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        l0 = be.launch_count()
+        l0 = be.launch_count() + (pp.replay_launches if pp else 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(be.stream)
+        t_issue = time.perf_counter()
         for _ in range(args.steps):
             step(a, b)
             a, b = b, a
         finish()  # the last exchange is inside the timed region
         e1.record(be.stream)
+        host_issue_ms = (time.perf_counter() - t_issue) * 1e3 / args.steps  # host time to ISSUE a step (no sync inside the loop)
         barrier()
         ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-        launches = be.launch_count() - l0
+        launches = be.launch_count() + (pp.replay_launches if pp else 0) - l0  # replayed graphs: the launches counted at their capture
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- dominant kernel alone (no collective): roofline ----
@@ -605,6 +612,8 @@ def main():
                             "over three streams and two device buffer sets (upload of step k+1 overlaps kernels and download of step k); "
                             "ms_per_step_unpipelined = the same calls back to back on one stream with a sync per step"},
             "gpu_launches": launches,
+            "host_issue_ms_per_step": host_issue_ms,
+            "cuda_graphs": bool(GRAPHS),
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved_min, "peak": peak, "unit": "GB/s", "frac": achieved_min / peak,
                          "traffic": ncu_traffic(kernel_name), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": ms_kernel, "kernel_ms_per_rank": kernel_ms_ranks, "note": ("rank-0 bytes, slowest rank's bandwidth; " if world > 1 else "") + roofline_note},

@@ -13,6 +13,7 @@ single-device.
 The partition helpers are pure index arithmetic on tensors and run on CPU tensors too (used by the gloo tests).
 """
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -247,6 +248,9 @@ class PipelinedPull:
         self.ev_done, self.ev_hub, self.ev_full = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.primed, self.k = False, 0
         self.recv_sym = None
+        self.graphs, self.last_dst = {}, None
+        self.graph_launches, self.replay_launches = {}, 0
+        self.use_graphs = os.environ.get("SPLA_B200_GRAPH", "1") == "1"
         if self.peers:
             # owner p writes its values for rank q at q's offset recv_off[q][p] of q's receive buffer (double-buffered by step parity:
             # a push for step k + 2 can only start after every rank has passed the hub barrier of step k + 1, i.e. after the scatter
@@ -271,6 +275,9 @@ class PipelinedPull:
         if not self.enabled:
             be.mxv_masked(M, src, self.mask_l, *self.ops, self.init, out=out)
             allgather_padded(dst, self.w, self.group)
+            return
+        if self.recv_sym is not None and self.peers.get(src.data_ptr()) is not None and self.peers.get(dst.data_ptr()) is not None:
+            self._step_peer(src, dst)
             return
         PRO, HUB, REST = 4, 1, 2
         be.mxv_masked_part(M, PRO, None, None, self.mask_l, *self.ops, self.init, out)
@@ -335,8 +342,107 @@ class PipelinedPull:
         self.primed = True
         self.k += 1
 
+    # ---- peer-mapped vectors: a step = (exchange of src, started first) beside (product into dst); one CUDA graph per direction ----
+    def _exchange_peer(self, vec, parity, hub):
+        """This rank's window of `vec` -> every peer's copy (copy engines, spread over the copy streams), closed by the device barrier of
+        the symmetric allocation on self.dma (-> ev_full); with `hub` also the owners' values of every rank's hub columns -> their
+        receive buffers, barrier, scatter into self.hub_vals on self.comm (-> ev_hub). Forked from the backend stream at the call."""
+        be, C = self.be, self.C
+        pv = self.peers[vec.data_ptr()]
+        self.ev_done.record(be.stream)
+        lanes = [self.dma] + self.dma_more
+        if hub:
+            self.comm.wait_event(self.ev_done)
+            be.v_gather(self.req, vec[self.w0:self.w0 + self.n_win], self.send, stream_ptr=self.comm_ptr)
+            rs = self.recv_sym[parity]
+            for d in range(self.world):
+                q = (self.rank + d) % self.world
+                if self.sc[q]:
+                    be._check(be.lib.splacu_memcpy_d2d(C.c_void_p(rs._ptrs[q] + self.recv_off[q] * 4), C.c_void_p(self.send.data_ptr() + self.send_off[q] * 4),
+                                                       self.sc[q] * 4, self.comm_ptr))
+            with torch.cuda.stream(self.comm):
+                rs.handle.barrier(channel=0)
+            be.v_scatter(self.order, rs.tensor, self.hub_vals, stream_ptr=self.comm_ptr)
+            self.ev_hub.record(self.comm)
+        for st in lanes:
+            st.wait_event(self.ev_done)
+        off, nbytes = self.w0 * 4, self.w * 4
+        for d in range(1, self.world):
+            p = (self.rank + d) % self.world
+            st = lanes[(d - 1) % len(lanes)]
+            be._check(be.lib.splacu_memcpy_d2d(C.c_void_p(pv._ptrs[p] + off), C.c_void_p(vec.data_ptr() + off), nbytes, C.c_void_p(st.cuda_stream)))
+        for st, ev in zip(self.dma_more, self.dma_more_ev):
+            ev.record(st)
+            self.dma.wait_event(ev)
+        with torch.cuda.stream(self.dma):
+            pv.handle.barrier(channel=1)
+        self.ev_full.record(self.dma)
+
+    def _body_peer(self, src, dst, parity):
+        be, M = self.be, self.M
+        out = dst[self.w0:self.w0 + self.n_win]
+        PRO, HUB, REST = 4, 1, 2
+        self._exchange_peer(src, parity, hub=True)
+        be.mxv_masked_part(M, PRO, None, None, self.mask_l, *self.ops, self.init, out)
+        be.stream.wait_event(self.ev_hub)
+        be.mxv_masked_part(M, HUB, None, self.hub_vals, self.mask_l, *self.ops, self.init, out)
+        be.stream.wait_event(self.ev_full)
+        be.mxv_masked_part(M, REST, src, None, self.mask_l, *self.ops, self.init, out)
+
+    def _step_peer(self, src, dst):
+        """Exchange-first step: src holds this rank's fresh window (the peers' windows may be stale); its exchange starts at once, the
+        mask pass runs beside it, the hub classes wait for the hub values, the rest for the windows. The sequence is fixed per
+        (src, dst), so after one eager run it is replayed as a CUDA graph: ~25 launches, copies and events per step cost one
+        cudaGraphLaunch on the host (a rank of an 8-GPU run computes for ~0.25 ms per step -- the Python issue loop is longer)."""
+        key = (src.data_ptr(), dst.data_ptr())
+        g = self.graphs.get(key)
+        if g is not None:
+            g.replay()
+            self.replay_launches += self.graph_launches[key]
+        else:
+            self._body_peer(src, dst, 0 if key[0] < key[1] else 1)
+        self.last_dst = dst
+        self.k += 1
+
+    def prepare(self, a, b):
+        """Collective: one eager step in each direction of the ping-pong (a -> b, b -> a; allocations and function attributes settle),
+        then both directions are captured as CUDA graphs. Without it (or with SPLA_B200_GRAPH=0) the steps stay eager."""
+        if not (self.enabled and self.use_graphs and self.recv_sym is not None and self.peers.get(a.data_ptr()) is not None
+                and self.peers.get(b.data_ptr()) is not None):
+            return False
+        self._step_peer(a, b)
+        self._step_peer(b, a)
+        self.finish()
+        ok = True
+        for src, dst in ((a, b), (b, a)):
+            key = (src.data_ptr(), dst.data_ptr())
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                l0 = self.be.launch_count()
+                with torch.cuda.graph(g, stream=self.be.stream, capture_error_mode="relaxed"):
+                    self._body_peer(src, dst, 0 if key[0] < key[1] else 1)
+                self.graphs[key] = g
+                self.graph_launches[key] = self.be.launch_count() - l0  # kernels of this library inside one replay
+            except Exception as ex:  # noqa: BLE001
+                ok = False
+                self.graphs.pop(key, None)
+                print(f"PipelinedPull rank {self.rank}: CUDA graph capture failed ({ex}); eager steps", file=sys.stderr)
+                torch.cuda.synchronize()
+        # all ranks or none: a rank replaying a graph and a rank issuing eagerly would still meet at the same barriers, but keep it uniform
+        flag = torch.tensor([1 if ok else 0], device=self.hub_cols.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if not bool(flag.item()):
+            self.graphs = {}
+        return bool(self.graphs)
+
     def finish(self):
         """the backend stream waits for the exchange of the last step (the vector is complete after this point in the stream)"""
+        if self.enabled and self.last_dst is not None:
+            self._exchange_peer(self.last_dst, 0, hub=False)
+            self.be.stream.wait_event(self.ev_full)
+            self.last_dst = None
+            return
         if self.enabled and self.primed:
             self.be.stream.wait_event(self.ev_hub)
             self.be.stream.wait_event(self.ev_full)
