@@ -243,6 +243,12 @@ SPLACU_API int splacu_v_assign_masked_sparse(int dtype, int op_assign, int op_se
 /* d_dst[k] = d_src[d_idx[k]] / d_dst[d_idx[k]] = d_src[k] for k < n, 4-byte elements (the hub-value exchange of the two-part product) */
 SPLACU_API int splacu_v_gather(uint32_t n, const uint32_t* d_idx, const void* d_src, void* d_dst, void* stream);
 SPLACU_API int splacu_v_scatter(uint32_t n, const uint32_t* d_idx, const void* d_src, void* d_dst, uint32_t n_dst, void* stream);
+/* element k of segment q (d_seg_off[q] <= k < d_seg_off[q + 1], n_peers segments): d_peer_dst[q][d_dst_idx[k]] = d_src[d_src_idx[k]].
+ * d_peer_dst is a DEVICE array of n_peers device pointers (peer-mapped buffers of the other GPUs of the box, or local ones): the owners'
+ * values of every rank's hub columns go straight into the peers' hub tables with NVLink stores -- one kernel instead of gather + n copies +
+ * scatter (spla_b200/dist.py:PipelinedPull). No reference counterpart (the reference is single-device). */
+SPLACU_API int splacu_v_push_peers(uint32_t n, const uint32_t* d_src_idx, const uint32_t* d_dst_idx, const uint32_t* d_seg_off, uint32_t n_peers,
+                                   void* const* d_peer_dst, const void* d_src, void* stream);
 SPLACU_API int splacu_v_pack_bits(int dtype, int op_select, uint32_t n, const void* d_v, uint32_t* d_bits, void* stream);
 SPLACU_API int splacu_v_unpack_bits(uint32_t n, const uint32_t* d_bits, uint32_t one_bits, uint32_t zero_bits, void* d_out, void* stream);
 /* number of entries != fill; reference src/cpu/cpu_v_count_mf.hpp:91-107, kernels/count.cl:46. Synchronises. */

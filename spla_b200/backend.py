@@ -45,7 +45,7 @@ SYMBOLS = [
     "splacu_dist_create", "splacu_dist_destroy", "splacu_dist_info", "splacu_dcsr_create", "splacu_dcsr_destroy", "splacu_dcsr_bounds",
     "splacu_dist_mxv_masked", "splacu_dist_vxm_masked_begin", "splacu_dist_vxm_masked_emit",
     "splacu_v_eadd_dense_op", "splacu_v_eadd_fdb_dense_op", "splacu_v_eadd_fdb_sparse_begin_op", "splacu_jit_compile", "splacu_jit_compile_count",
-    "splacu_csr_hub_cols", "splacu_mxv_masked_part", "splacu_v_gather", "splacu_v_scatter",
+    "splacu_csr_hub_cols", "splacu_mxv_masked_part", "splacu_v_gather", "splacu_v_scatter", "splacu_v_push_peers",
 ]
 
 
@@ -129,6 +129,7 @@ def load_library(build_if_missing=True):
         "splacu_jit_compile": [i32, pop, pop, pop, C.POINTER(C.c_size_t)], "splacu_jit_compile_count": [C.POINTER(C.c_uint64)],
         "splacu_csr_hub_cols": [vp, pu32, C.POINTER(vp)], "splacu_mxv_masked_part": [vp, i32, i32, i32, i32, vp, vp, vp, vp, u32, i32, vp],
         "splacu_v_gather": [u32, vp, vp, vp, vp], "splacu_v_scatter": [u32, vp, vp, vp, u32, vp],
+        "splacu_v_push_peers": [u32, vp, vp, vp, u32, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -355,6 +356,12 @@ class Backend:
     def v_scatter(self, idx, src, dst, stream_ptr=None):
         self._check(self.lib.splacu_v_scatter(idx.numel(), _ptr(idx), _ptr(src), _ptr(dst), dst.numel(), stream_ptr if stream_ptr is not None else self.stream_ptr))
         return dst
+
+    def v_push_peers(self, src_idx, dst_idx, seg_off, peer_ptrs, src, stream_ptr=None):
+        """peer_ptrs[q][dst_idx[k]] = src[src_idx[k]] for the elements k of segment q (seg_off: int32 [n_peers + 1], peer_ptrs: int64
+        device tensor of n_peers device pointers)"""
+        self._check(self.lib.splacu_v_push_peers(src_idx.numel(), _ptr(src_idx), _ptr(dst_idx), _ptr(seg_off), peer_ptrs.numel(), _ptr(peer_ptrs), _ptr(src),
+                                                 stream_ptr if stream_ptr is not None else self.stream_ptr))
 
     def vxm_masked(self, M, vi, vx, mask, op_mult, op_add, op_select, out=None):
         """r = v x M (push) over the sparse vector (vi, vx). Mirrors exec_vxm_masked(r, mask, v, M, ...).

@@ -236,6 +236,19 @@ namespace splacu {
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) dst[k] = src[idx[k]];
     }
 
+    // element k of segment q (seg_off[q] <= k < seg_off[q + 1]): peer_dst[q][dst_idx[k]] = src[src_idx[k]] -- a gather from the local
+    // vector stored straight into the peers' buffers (NVLink peer stores when peer_dst[q] is peer-mapped memory)
+    __global__ void __launch_bounds__(kBlock) push_peers_kernel(uint32_t n, const uint32_t* __restrict__ src_idx, const uint32_t* __restrict__ dst_idx,
+                                                                const uint32_t* __restrict__ seg_off, uint32_t n_peers, uint32_t* const* __restrict__ peer_dst,
+                                                                const uint32_t* __restrict__ src) {
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+            uint32_t q = 0;
+            while (q + 1 < n_peers && k >= seg_off[q + 1]) ++q;
+            peer_dst[q][dst_idx[k]] = src[src_idx[k]];
+        }
+    }
+
     // dense -> bitmap of entries != fill (value comparison in T). One warp ballot = one bitmap word.
     template<typename T>
     __global__ void __launch_bounds__(kBlock) mark_nonfill_kernel(const T* __restrict__ dense, uint32_t n, T fill, uint32_t* __restrict__ bitmap) {
@@ -477,6 +490,18 @@ int splacu_v_gather(uint32_t n, const uint32_t* d_idx, const void* d_src, void* 
     SPLACU_REQUIRE(d_idx && d_src && d_dst, "null pointer");
     cudaStream_t s = resolve_stream(stream);
     gather_kernel<<<grid_for(n, kBlock, 8), kBlock, 0, s>>>(n, d_idx, static_cast<const uint32_t*>(d_src), static_cast<uint32_t*>(d_dst));
+    SPLACU_LAUNCH_CHECK();
+    return SPLACU_OK;
+}
+
+int splacu_v_push_peers(uint32_t n, const uint32_t* d_src_idx, const uint32_t* d_dst_idx, const uint32_t* d_seg_off, uint32_t n_peers,
+                        void* const* d_peer_dst, const void* d_src, void* stream) {
+    SPLACU_CHECK_INIT();
+    if (n == 0) return SPLACU_OK;
+    SPLACU_REQUIRE(d_src_idx && d_dst_idx && d_seg_off && d_peer_dst && d_src && n_peers > 0, "null pointer");
+    cudaStream_t s = resolve_stream(stream);
+    push_peers_kernel<<<grid_for(n, kBlock, 8), kBlock, 0, s>>>(n, d_src_idx, d_dst_idx, d_seg_off, n_peers, reinterpret_cast<uint32_t* const*>(d_peer_dst),
+                                                               static_cast<const uint32_t*>(d_src));
     SPLACU_LAUNCH_CHECK();
     return SPLACU_OK;
 }

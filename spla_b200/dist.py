@@ -186,6 +186,7 @@ def hub_exchange_plan(hub_cols, w, group=None):
       recv_counts  list [world]   values this rank receives from each owner
       req          int32 [...]    offsets into THIS rank's window that the other ranks ask for, grouped by requester
       send_counts  list [world]   how many of them go to each requester
+      dst_slot     int32 [...]    for every element of req: the slot of the REQUESTER's hub table it fills (splacu_v_push_peers)
     Pure index arithmetic + two small all-to-all exchanges (runs on gloo with CPU tensors, too)."""
     world = dist.get_world_size(group)
     cols = hub_cols.to(torch.int64)
@@ -198,7 +199,10 @@ def hub_exchange_plan(hub_cols, w, group=None):
     rc, sc = [int(x) for x in recv_counts.tolist()], [int(x) for x in send_counts.tolist()]
     req = torch.empty(sum(sc), dtype=torch.int32, device=hub_cols.device)
     dist.all_to_all_single(req, offs, output_split_sizes=sc, input_split_sizes=rc, group=group)
-    return {"order": order, "recv_counts": rc, "req": req, "send_counts": sc}
+    # where the requester wants every value: slot order[j] of its hub table for its j-th received value (sent back grouped like req)
+    dst_slot = torch.empty(sum(sc), dtype=torch.int32, device=hub_cols.device)
+    dist.all_to_all_single(dst_slot, order.to(torch.int32).contiguous(), output_split_sizes=sc, input_split_sizes=rc, group=group)
+    return {"order": order, "recv_counts": rc, "req": req, "send_counts": sc, "dst_slot": dst_slot}
 
 
 class PipelinedPull:
@@ -242,7 +246,8 @@ class PipelinedPull:
         self.comm, self.dma = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         self.comm_ptr, self.dma_ptr = C.c_void_p(self.comm.cuda_stream), C.c_void_p(self.dma.cuda_stream)
         # further copy streams: the peer copies of one step are spread over them so that several copy engines work at once
-        n_dma = max(1, min(int(os.environ.get("SPLA_B200_DMA_STREAMS", "4")), self.world - 1))
+        # (default 1: on 8 GPUs one stream of 7 copies measured 0.446 ms per step, four streams 0.469)
+        n_dma = max(1, min(int(os.environ.get("SPLA_B200_DMA_STREAMS", "1")), self.world - 1))
         self.dma_more = [torch.cuda.Stream(device=dev) for _ in range(n_dma - 1)]
         self.dma_more_ev = [torch.cuda.Event() for _ in self.dma_more]
         self.ev_done, self.ev_hub, self.ev_full = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
@@ -250,6 +255,10 @@ class PipelinedPull:
         self.recv_sym = None
         self.graphs, self.last_dst = {}, None
         self.graph_launches, self.replay_launches = {}, 0
+        # transport of the windows in the peer-mapped flow: "dma" = peer copies on the copy engines, "nccl" = in-place ncclAllGather
+        # (default "dma": measured on 2 and 8 B200s; "nccl" inside the graph was only run on 2 GPUs -- 0.759 ms against 0.716 -- and is opt-in)
+        self.win_nccl = os.environ.get("SPLA_B200_WIN", "dma") == "nccl"
+        self.win_group = None
         self.use_graphs = os.environ.get("SPLA_B200_GRAPH", "1") == "1"
         if self.peers:
             # owner p writes its values for rank q at q's offset recv_off[q][p] of q's receive buffer (double-buffered by step parity:
@@ -264,6 +273,17 @@ class PipelinedPull:
             for q in range(1, self.world):
                 self.send_off[q] = self.send_off[q - 1] + self.sc[q - 1]
             self.recv_sym = [PeerVector(backend, n_hub_max, group=group), PeerVector(backend, n_hub_max, group=group)]
+            if self.win_nccl:  # its own communicator (and NCCL stream) beside whatever else the caller runs on the default group
+                self.win_group = dist.new_group(backend=dist.get_backend(group))
+            # direct form (default): one kernel stores the requested values straight into the requesters' hub tables (recv_sym used as the
+            # table itself, slot order) -- no copies, no scatter; SPLA_B200_HUB_PUSH=0 keeps gather + copies + scatter
+            self.hub_push = os.environ.get("SPLA_B200_HUB_PUSH", "1") == "1"
+            self.dst_slot = plan["dst_slot"].contiguous()
+            so = [0] * (self.world + 1)
+            for q in range(self.world):
+                so[q + 1] = so[q] + self.sc[q]
+            self.seg_off = torch.tensor(so, dtype=torch.int32, device=dev)
+            self.peer_tabs = [torch.tensor([int(x) for x in rs.handle.buffer_ptrs], dtype=torch.int64, device=dev) for rs in self.recv_sym]
         else:
             self.recv = torch.empty(n_hub, dtype=torch.float32, device=dev)
             self.small = dist.new_group(backend=dist.get_backend(group))  # its own communicator: runs beside the big all-gather
@@ -351,7 +371,16 @@ class PipelinedPull:
         pv = self.peers[vec.data_ptr()]
         self.ev_done.record(be.stream)
         lanes = [self.dma] + self.dma_more
-        if hub:
+        if hub and self.hub_push:
+            self.comm.wait_event(self.ev_done)
+            rs = self.recv_sym[parity]
+            be.v_push_peers(self.req, self.dst_slot, self.seg_off, self.peer_tabs[parity], vec[self.w0:self.w0 + self.n_win], stream_ptr=self.comm_ptr)
+            with torch.cuda.stream(self.comm):
+                rs.handle.barrier(channel=0)
+            self.ev_hub.record(self.comm)
+            self.cur_hub = rs.tensor
+        elif hub:
+            self.cur_hub = self.hub_vals
             self.comm.wait_event(self.ev_done)
             be.v_gather(self.req, vec[self.w0:self.w0 + self.n_win], self.send, stream_ptr=self.comm_ptr)
             rs = self.recv_sym[parity]
@@ -364,6 +393,14 @@ class PipelinedPull:
                 rs.handle.barrier(channel=0)
             be.v_scatter(self.order, rs.tensor, self.hub_vals, stream_ptr=self.comm_ptr)
             self.ev_hub.record(self.comm)
+        if self.win_nccl:
+            # the windows by the collective library (in place, equal windows): on 8 GPUs its all-gather (NVLS multicast) is faster than
+            # 7 peer copies per rank; captured into the step's graph like everything else
+            self.dma.wait_event(self.ev_done)
+            with torch.cuda.stream(self.dma):
+                dist.all_gather_into_tensor(vec[:self.world * self.w], vec[self.w0:self.w0 + self.w], group=self.win_group)
+            self.ev_full.record(self.dma)
+            return
         for st in lanes:
             st.wait_event(self.ev_done)
         off, nbytes = self.w0 * 4, self.w * 4
@@ -385,7 +422,7 @@ class PipelinedPull:
         self._exchange_peer(src, parity, hub=True)
         be.mxv_masked_part(M, PRO, None, None, self.mask_l, *self.ops, self.init, out)
         be.stream.wait_event(self.ev_hub)
-        be.mxv_masked_part(M, HUB, None, self.hub_vals, self.mask_l, *self.ops, self.init, out)
+        be.mxv_masked_part(M, HUB, None, self.cur_hub, self.mask_l, *self.ops, self.init, out)
         be.stream.wait_event(self.ev_full)
         be.mxv_masked_part(M, REST, src, None, self.mask_l, *self.ops, self.init, out)
 

@@ -256,6 +256,14 @@ def _hub_plan_worker(rank, world, port, out_dir):
         hub_vals = torch.full((hub_cols.numel(),), -7, dtype=torch.int32)
         hub_vals[plan["order"]] = recv  # splacu_v_scatter
         assert torch.equal(hub_vals, v_full[hub_cols.long()]), "hub values gathered from their owners differ from v[hub_cols]"
+        # the direct form (splacu_v_push_peers): the owner stores value k into slot dst_slot[k] of the requester's table; emulate the
+        # peer stores by shipping the slots beside the values
+        assert plan["dst_slot"].numel() == plan["req"].numel()
+        slots = torch.empty(hub_cols.numel(), dtype=torch.int32)
+        dist.all_to_all_single(slots, plan["dst_slot"].contiguous(), output_split_sizes=plan["recv_counts"], input_split_sizes=plan["send_counts"])
+        table = torch.full((hub_cols.numel(),), -7, dtype=torch.int32)
+        table[slots.long()] = recv
+        assert torch.equal(table, v_full[hub_cols.long()]), "hub values pushed into the requesters' slots differ from v[hub_cols]"
         open(os.path.join(out_dir, f"hub_ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

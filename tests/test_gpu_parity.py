@@ -816,3 +816,25 @@ def test_pull_two_part_product(backend, oracle, dtype, om, oa, osel, slots, col_
         backend.sync()
         assert_values(to_np(out, cases.NP[dtype]), want, cases.exact_expected(dtype, om, oa), what=f"two-part mxv rep {rep}",
                       bound=lambda: mxv_bound(om, oa, Ap, Aj, Ax, v, init))
+
+
+@pytest.mark.gpu
+def test_v_push_peers_local(backend):
+    """splacu_v_push_peers with every 'peer' buffer on this device: segment q of the element list lands in buffer q at the given slots."""
+    g = torch.Generator(device=backend.device)
+    g.manual_seed(5)
+    n_src, n_peers, n_dst = 5000, 3, 700
+    src = torch.randint(-1000, 1000, (n_src,), generator=g, device=backend.device, dtype=torch.int32)
+    counts = [300, 0, 700]
+    seg_off = torch.tensor([0, 300, 300, 1000], dtype=torch.int32, device=backend.device)
+    src_idx = torch.randint(0, n_src, (1000,), generator=g, device=backend.device, dtype=torch.int32)
+    dst_idx = torch.cat([torch.randperm(n_dst, generator=g, device=backend.device)[:c] for c in counts]).to(torch.int32)
+    bufs = [torch.full((n_dst,), -7, dtype=torch.int32, device=backend.device) for _ in range(n_peers)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=backend.device)
+    backend.v_push_peers(src_idx, dst_idx, seg_off, ptrs, src)
+    backend.sync()
+    for q in range(n_peers):
+        want = torch.full((n_dst,), -7, dtype=torch.int32, device=backend.device)
+        a, b = int(seg_off[q]), int(seg_off[q + 1])
+        want[dst_idx[a:b].long()] = src[src_idx[a:b].long()]
+        assert torch.equal(bufs[q], want), f"buffer {q}"
