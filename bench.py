@@ -589,10 +589,10 @@ def main():
             row_desc = (f"; mxv_scat_kernel x {len(row_nnz)} row classes of the tail (entry shares " + ", ".join(f"{x / max(1, nnz_l):.3f}" for x in row_nnz) +
                         f"; {sum(csr_info.get('row_class_rows') or [])} rows accumulate in shared-memory tables while v streams) + merge kernel per class")
         kernel_desc = (f"mxv_seg_kernel x {len(phase_nnz)} column classes (entry shares {shares}; {csr_info['n_hub']} hub columns in shared-memory "
-                       f"tables of 16-bit slots, tail class gathers v) + mxv_seg_fixup_kernel per class" + row_desc)
-        roofline_note = (f"one step = one splacu_mxv_masked call = {len(phase_nnz)} launches of mxv_seg_kernel (one per column class) with their fix-ups, "
+                       f"tables of 16-bit slots, tail class gathers v) + one two-launch fix-up of the rows that span tiles" + row_desc)
+        roofline_note = (f"one step = one splacu_mxv_masked call = {len(phase_nnz)} launches of mxv_seg_kernel (one per column class), the two fix-up launches (chain sums, rows), "
                          f"{len(row_nnz)} launches of mxv_scat_kernel (row classes of the tail) with their merges, "
-                         "the mask-count / fill pass and the hub pack; achieved = algorithmic bytes of the step / its device time, traffic = DRAM bytes "
+                         "the mask-count / fill pass (it also packs the hub values) and the gated CSR pass idling on a side stream; achieved = algorithmic bytes of the step / its device time, traffic = DRAM bytes "
                          "of all launches of the step")
     else:
         kernel_name = "mxv_wtile_kernel"

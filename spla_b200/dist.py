@@ -411,6 +411,11 @@ class PipelinedPull:
         for st, ev in zip(self.dma_more, self.dma_more_ev):
             ev.record(st)
             self.dma.wait_event(ev)
+        if hub:
+            # the two device barriers of a step spin on the peers: keep them in ONE order on every rank (hub barrier, then window barrier)
+            # -- independent branches of a graph are not guaranteed to run concurrently, and two ranks that serialised them in opposite
+            # orders would wait for each other forever
+            self.dma.wait_event(self.ev_hub)
         with torch.cuda.stream(self.dma):
             pv.handle.barrier(channel=1)
         self.ev_full.record(self.dma)
