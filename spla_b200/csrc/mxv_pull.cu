@@ -1082,6 +1082,19 @@ namespace splacu {
         }
     }
 
+    // select = ALWAYS (no mask pass): r = init and the hub pack in one launch (the PageRank step of spla::pr, src/algorithm.cpp:312)
+    template<typename T>
+    __global__ void __launch_bounds__(kBlock) fill_pack_kernel(T* __restrict__ r, T init, uint32_t n, uint32_t n_main, const uint32_t* __restrict__ hub_cols,
+                                                               uint32_t n_hub, const uint32_t* __restrict__ v, uint32_t* __restrict__ hub_vals) {
+        if (blockIdx.x >= n_main) {
+            const uint32_t q = (blockIdx.x - n_main) * blockDim.x + threadIdx.x;
+            if (q < n_hub) hub_vals[q] = __ldg(v + hub_cols[q]);
+            return;
+        }
+        const uint32_t stride = n_main * blockDim.x;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) r[i] = init;
+    }
+
     template<typename T, typename S, bool MASKED, int MODE, int WARPS>
     static int launch_wtile(S sr, Select sel, const TileJob& job, const T* v, const T* mask, T* r, T init, cudaStream_t s) {
         auto           kern = mxv_wtile_kernel<T, S, MASKED, MODE, WARPS>;
@@ -1147,9 +1160,10 @@ namespace splacu {
             if ((rc = set_persisting_window(v, (size_t) M->n_cols * 4, s))) return rc;
         const bool seg_classes = M->n_phases && M->phase[0].seg;
         const bool fuse_pack   = seg_classes && M->n_hub && parts == 7 && !d_hub_vals && sel.reads_mask && M->sel_count;// packed by the mask pass below
+        const bool fuse_fill   = seg_classes && M->n_hub && parts == 7 && !d_hub_vals && !(sel.reads_mask && M->sel_count);// packed by the fill of r
         if (M->n_hub && (parts & 1) && d_hub_vals) {// the caller brings the hub values (gathered from their owners)
             SPLACU_CUDA(cudaMemcpyAsync(M->hub_vals, d_hub_vals, (size_t) M->n_hub * 4, cudaMemcpyDeviceToDevice, s));
-        } else if (M->n_hub && (parts & 1) && !fuse_pack) {
+        } else if (M->n_hub && (parts & 1) && !fuse_pack && !fuse_fill) {
             SPLACU_PROFILE("splacu/mxv/hub_pack", s);
             mxv_hub_pack_kernel<<<(M->n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(M->hub_cols, M->n_hub, reinterpret_cast<const uint32_t*>(v), M->hub_vals);
             SPLACU_LAUNCH_CHECK();
@@ -1194,6 +1208,14 @@ namespace splacu {
                     cudaStreamWaitEvent(s, M->ev_join, 0);
                     return rc;
                 }
+            }
+            if (fuse_fill) {
+                SPLACU_PROFILE("splacu/mxv/fill_pack", s);
+                const uint32_t n_main = (uint32_t) grid_for(M->n_rows, kBlock, 8);
+                fill_pack_kernel<T><<<n_main + (M->n_hub + kBlock - 1) / kBlock, kBlock, 0, s>>>(r, init, M->n_rows, n_main, M->hub_cols, M->n_hub,
+                                                                                               reinterpret_cast<const uint32_t*>(v), M->hub_vals);
+                SPLACU_LAUNCH_CHECK();
+                parts = 3;// the prologue is done
             }
             rc = seg_mxv(M, TypeCode<T>::value, sr.mult_op(), sr.add_op(), sel, v, mask, r, to_bits(init), gate, gate_min, s, parts);
             if (side) SPLACU_CUDA(cudaStreamWaitEvent(s, M->ev_join, 0));

@@ -206,19 +206,25 @@ def hub_exchange_plan(hub_cols, w, group=None):
 
 
 class PipelinedPull:
-    """Row-sharded pull (one process per GPU) whose exchange overlaps the next step's hub class passes.
+    """Row-sharded pull (one process per GPU) whose exchange overlaps the product.
 
     A plain step is: local product -> all-gather of the windows -> next step. The hub classes of the product (63 % of the entries of
-    an RMAT matrix) read only the ~180 K most referenced elements of v, though, so after its local product a rank (1) sends the
-    owners' values of every rank's hub columns (< 1 MB per rank) and (2) starts the exchange of the windows; the next step's hub
-    classes (splacu_mxv_masked_part) run as soon as (1) has landed, the rest (row classes, tail classes, fix-ups) when (2) has; the
-    prologue (mask pass) waits for nothing. Same results as the plain step up to the order in which the classes add onto r.
+    an RMAT matrix) read only the ~180 K most referenced elements of v, though, so the owners' values of every rank's hub columns
+    (< 1 MB per rank) travel first and the hub classes (splacu_mxv_masked_part) start on them while the windows are still in flight;
+    the rest (row classes, tail classes, fix-ups) waits for the windows, the prologue (mask pass) for nothing. Same results as the plain
+    step (the classes add onto r in the same order).
 
-    Transport. With peer-mapped vectors (`peers`: {tensor.data_ptr(): PeerVector}) both exchanges are cudaMemcpyAsync peer copies on the
-    copy engines over NVLink, each closed by the device-side barrier of a symmetric allocation: no SM is taken from the persistent class
-    kernels of the next product. An NCCL all-gather kernel running beside them does take SMs, and their CTAs need a whole SM each, so
-    every SM NCCL holds delays one CTA -- and with it the kernel (2 GPUs, RMAT-24: 0.839 ms plain, 0.819 overlapped over NCCL, 0.789
-    with peer copies). Without peer-mapped vectors: a small all-to-all + ncclAllGather on two communicators."""
+    Two flows:
+      * peer-mapped vectors (`peers`: {tensor.data_ptr(): PeerVector}; the default of bench.py): EXCHANGE-FIRST steps. step(src, dst)
+        begins with the exchange of src -- whose own window the previous step produced -- and computes dst's window beside it:
+        hub values by one kernel of NVLink peer stores straight into the peers' hub tables (splacu_v_push_peers), windows as
+        cudaMemcpyAsync peer copies on the copy engines, each closed by the device barrier of a symmetric allocation (no SM is taken from
+        the persistent class kernels: an NCCL kernel beside them delays one class CTA per SM it holds). prepare(a, b) captures both
+        directions of the ping-pong as CUDA graphs, so a step costs the host one cudaGraphLaunch instead of ~25 launches, copies and
+        event operations. finish() exchanges the last result. Measured on RMAT-24 (profiles/r02_bench_multi_gpu.txt): 0.732 ms on 2,
+        0.453 ms on 4, 0.3245 ms on 8 B200s against 1.302 ms on one.
+      * without peer-mapped vectors: EXCHANGE-LAST steps over the collective library (a small all-to-all for the hub values + an in-place
+        ncclAllGather of the windows on two communicators, started after the product and awaited by the next step's parts)."""
 
     def __init__(self, backend, M, w, w0, n_win, ops, init, mask_l, group=None, peers=None):
         import ctypes as C
