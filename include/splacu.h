@@ -80,7 +80,15 @@ SPLACU_API int         splacu_launch_count(uint64_t* count); /* kernels launched
  * "mxv_red" (read per call, default 1) = the class passes of a PLUS semiring add their row sums onto r with reductions at the L2
  * (red.global.add) instead of load + add + store. Integer results are unchanged; FLOAT results keep the same two-operand rounding and
  * the same fixed order, but red.global.add.f32 flushes subnormal operands and sums to zero (PTX ISA), where the reference keeps
- * them: set 0 when |r| < 1.2e-38 matters. Also from the environment: SPLACU_OPTIONS="name=value,..." */
+ * them: set 0 when |r| < 1.2e-38 matters.
+ * "mxv_fixup_merge" (per call, default 2) = how the partial sums of rows that span tiles are folded in: 2 = two plain launches (all chain
+ * sums, then one thread per row in class order), 1 = one cooperative launch with a grid barrier per class, 0 = one launch per class;
+ * 2 and 1 add in the same order (bit-identical results). "mxv_bank_order" (at handle creation, default 1) = permute the entries of a row
+ * run inside a lane of a hub class against shared-memory bank conflicts. "mxv_reserve_sms" (per call, default 0) = SMs the persistent
+ * class kernels leave free for the kernels of a collective running beside them.
+ * A product on a handle with column classes forks the handle's side stream from the caller's stream and joins it before it returns
+ * control of the stream (the mask-first CSR pass runs there): to the caller the call is still ordered on the one stream it passed.
+ * Also from the environment: SPLACU_OPTIONS="name=value,..." */
 SPLACU_API int         splacu_set_option(const char* name, int64_t value);
 SPLACU_API int         splacu_get_option(const char* name, int64_t* value);
 
