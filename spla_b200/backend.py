@@ -72,7 +72,7 @@ class SplacuError(RuntimeError):
 
 def load_library(build_if_missing=True):
     """dlopen spla_b200/lib/libsplacu.so; build it with nvcc first if it is not there. Never falls back."""
-    path = _build.LIB
+    path = os.environ.get("SPLACU_LIB") or _build.LIB  # SPLACU_LIB: an experimental build of the same sources (tools/ A/B runs)
     if not os.path.exists(path):
         if not build_if_missing:
             raise SplacuError(f"{path} is missing: run `python -m spla_b200.build`")

@@ -26,7 +26,10 @@
 namespace splacu {
 
     static constexpr int kBlock = 256;
-    static constexpr int kEpt   = 8;// edge slots per thread per chunk
+#ifndef SPLACU_VXM_EPT
+#define SPLACU_VXM_EPT 4
+#endif
+    static constexpr int kEpt   = SPLACU_VXM_EPT;// edge slots per thread per chunk (4: measured against 2 / 8 / 16, profiles/r02_exp_notes.txt)
 
     // deg[t] = length of row vi[t]; optionally also rowstart[t] = Ap[vi[t]] (so that the expand reads it sequentially instead of
     // chasing vi -> Ap) and *differs |= (vx[t] != vx[0]) (bit patterns): the structure-only push needs one frontier value
