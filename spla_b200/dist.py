@@ -221,7 +221,7 @@ class PipelinedPull:
         cudaMemcpyAsync peer copies on the copy engines, each closed by the device barrier of a symmetric allocation (no SM is taken from
         the persistent class kernels: an NCCL kernel beside them delays one class CTA per SM it holds). prepare(a, b) captures both
         directions of the ping-pong as CUDA graphs, so a step costs the host one cudaGraphLaunch instead of ~25 launches, copies and
-        event operations. finish() exchanges the last result. Measured on RMAT-24 (profiles/r02_bench_multi_gpu.txt): 0.732 ms on 2,
+        event operations. finish() exchanges the last result. Measured on RMAT-24 (profiles/r02_bench_multi_gpu.txt): 0.717 ms on 2,
         0.453 ms on 4, 0.3245 ms on 8 B200s against 1.302 ms on one.
       * without peer-mapped vectors: EXCHANGE-LAST steps over the collective library (a small all-to-all for the hub values + an in-place
         ncclAllGather of the windows on two communicators, started after the product and awaited by the next step's parts)."""
