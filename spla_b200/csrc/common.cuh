@@ -170,7 +170,7 @@ namespace splacu {
     static constexpr int kMxvTile = 512;// nnz per warp tile of the streaming pull kernel
 
     // ---- tuning options (splacu_set_option) -------------------------------------------------
-    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_MXV_RED, OPT_MXV_ROW_CLASSES, OPT_MXV_ROW_MIN_COUNT, OPT_MXV_FIXUP_MERGE, OPT_MXV_ROW_MIN_NNZ, OPT_MXV_BANK_ORDER, OPT_MXV_RESERVE_SMS, OPT_COUNT };
+    enum Option { OPT_MXV_HUB = 0, OPT_MXV_HUB_MIN_COUNT, OPT_MXV_HUB_TOTAL, OPT_MXV_HUB_SMEM, OPT_MXV_L2_PERSIST, OPT_VXM_SELBITS, OPT_MXV_PHASES, OPT_MXV_PHASE_SLOTS, OPT_MXV_PHASE_ONLY, OPT_MXV_SEG, OPT_MXV_SEG_MIN_DENSITY, OPT_MXV_TAIL_RANGE_LOG2, OPT_SMALL_FRONT, OPT_VXM_STRUCT, OPT_MXV_RED, OPT_MXV_ROW_CLASSES, OPT_MXV_ROW_MIN_COUNT, OPT_MXV_FIXUP_MERGE, OPT_MXV_ROW_MIN_NNZ, OPT_MXV_BANK_ORDER, OPT_MXV_RESERVE_SMS, OPT_MXV_PDL, OPT_COUNT };
     int64_t get_option(int opt);
     // CTAs of a persistent one-CTA-per-SM kernel of the pull product: all SMs but the ones option mxv_reserve_sms keeps free
     inline uint32_t persistent_grid_cap() {

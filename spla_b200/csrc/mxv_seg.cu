@@ -361,6 +361,10 @@ namespace splacu {
         };
         load_meta(first);
         prefetch(first);
+        // Programmatic dependent launch (option mxv_pdl): this CTA may have been scheduled while the last CTAs of the previous class pass
+        // were still running -- everything above read only the matrix and the packed hub values. r, head / tail and the selection bitmap
+        // are touched below: wait until the previous grid has completed and its writes are visible (a no-op in a plain launch).
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 
         for (uint32_t tile = first; tile < n_tiles; tile += n_warps) {
             const uint32_t base = sb0, nfl = sb1 - sb0;
@@ -741,9 +745,29 @@ namespace splacu {
         const int p = (int) (&ph - M->phase);
         {
             SPLACU_PROFILE(kLabels[0][p], s);
-            kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
-                                                    ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
-            SPLACU_LAUNCH_CHECK();
+            // (not in the parts of a split product: those are captured into the CUDA graphs of the multi-GPU step, whose capture was
+            //  measured and verified without programmatic edges)
+            if (get_option(OPT_MXV_PDL) && !g_split_call) {
+                cudaLaunchConfig_t  cfg = {};
+                cudaLaunchAttribute attr[1];
+                cfg.gridDim          = dim3((unsigned) grid);
+                cfg.blockDim         = dim3(kW * 32);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream           = s;
+                attr[0].id           = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs    = attr;
+                cfg.numAttrs = 1;
+                SPLACU_CUDA(cudaLaunchKernelEx(&cfg, kern, sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), static_cast<const uint32_t*>(ph.Ax),
+                                               static_cast<const uint32_t*>(ph.flags), static_cast<const uint32_t*>(ph.seg_base),
+                                               static_cast<const uint32_t*>(ph.seg_row), static_cast<const uint32_t*>(ph.chain), ph.head, ph.tail, v, sel_bits, r,
+                                               ph.n_tiles, static_cast<const uint32_t*>(M->hub_vals + ph.slot_base), ph.n_slots, gate, gate_min));
+                count_launch(1);
+            } else {
+                kern<<<grid, kW * 32, smem, s>>>(sr, sel, reinterpret_cast<const uint32_t*>(ph.Aj), ph.Ax, ph.flags, ph.seg_base, ph.seg_row, ph.chain, ph.head,
+                                                        ph.tail, v, sel_bits, r, ph.n_tiles, M->hub_vals + ph.slot_base, ph.n_slots, gate, gate_min);
+                SPLACU_LAUNCH_CHECK();
+            }
         }
         if (!get_option(OPT_MXV_FIXUP_MERGE) && !g_split_call) {
             SPLACU_PROFILE(kLabels[1][p], s);

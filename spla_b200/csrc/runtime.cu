@@ -37,8 +37,8 @@ namespace splacu {
         return (int) e;
     }
 
-    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1, /*mxv_red: hub class passes of a PLUS semiring add their segment sums onto r with L2 reductions (red.add) instead of load + add + store; FLOAT: red.global.add.f32 flushes subnormal sums to zero (PTX ISA), 0 keeps them*/ 1, /*mxv_row_classes: row classes of the tail (the tail entries of the rows with the most of them, scattered into a shared-memory table of partial results while v streams)*/ 1, /*mxv_row_min_count: tail entries a row needs to get a slot*/ 64, /*mxv_fixup_merge: 0 one fix-up launch per class, 1 the fix-ups of all classes in one cooperative launch after the last class pass (grid barrier between classes, fixed order), 2 two plain launches: all chain sums at once, then one thread per row adds them in class order (same order as 1: bit-identical)*/ 2, /*mxv_row_min_nnz: entries a row class must hold to be built (its fixed costs against ~2 ps saved per entry)*/ 25165824, /*mxv_bank_order: at handle build, permute the entries of every row run inside a lane of a hub class against shared-memory bank conflicts of the table gathers*/ 1, /*mxv_reserve_sms: SMs the persistent class kernels of the pull product leave free (for the kernels of a collective that runs beside them in a multi-GPU step)*/ 0};
-    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct", "mxv_red", "mxv_row_classes", "mxv_row_min_count", "mxv_fixup_merge", "mxv_row_min_nnz", "mxv_bank_order", "mxv_reserve_sms"};
+    static int64_t g_options[OPT_COUNT] = {/*mxv_hub: 0 off, 1 auto (column-class phases), 2 force the single-pass hub cache, 3 force phases*/ 1, /*mxv_hub_min_count*/ 16, /*mxv_hub_total*/ 1048576, /*mxv_hub_smem*/ 16384, /*mxv_l2_persist*/ 0, /*vxm_selbits*/ 1, /*mxv_phases*/ 4, /*mxv_phase_slots*/ 45056, /*mxv_phase_only: profiling aid, p + 1 runs class p alone (wrong result)*/ 0, /*mxv_seg: classes in the segmented-tile format*/ 1, /*mxv_seg_min_density: percent of rows a mask must select for the class passes*/ 45, /*mxv_tail_range_log2: the tail class is split into windows of 2^k columns of v (one pass each, L2-resident gathers)*/ 24, /*small_front: single-CTA offset / emit / filter kernels for fronts of <= 8192 entries (launch-latency paths)*/ 1, /*vxm_struct: structure-only push when every product is provably the same value and the add is idempotent*/ 1, /*mxv_red: hub class passes of a PLUS semiring add their segment sums onto r with L2 reductions (red.add) instead of load + add + store; FLOAT: red.global.add.f32 flushes subnormal sums to zero (PTX ISA), 0 keeps them*/ 1, /*mxv_row_classes: row classes of the tail (the tail entries of the rows with the most of them, scattered into a shared-memory table of partial results while v streams)*/ 1, /*mxv_row_min_count: tail entries a row needs to get a slot*/ 64, /*mxv_fixup_merge: 0 one fix-up launch per class, 1 the fix-ups of all classes in one cooperative launch after the last class pass (grid barrier between classes, fixed order), 2 two plain launches: all chain sums at once, then one thread per row adds them in class order (same order as 1: bit-identical)*/ 2, /*mxv_row_min_nnz: entries a row class must hold to be built (its fixed costs against ~2 ps saved per entry)*/ 25165824, /*mxv_bank_order: at handle build, permute the entries of every row run inside a lane of a hub class against shared-memory bank conflicts of the table gathers*/ 1, /*mxv_reserve_sms: SMs the persistent class kernels of the pull product leave free (for the kernels of a collective that runs beside them in a multi-GPU step)*/ 0, /*mxv_pdl: the class passes are launched with programmatic stream serialization: the CTAs of the next pass load their hub table and first tile while the last CTAs of the previous pass finish, and wait (griddepcontrol.wait) before they touch r*/ 1};
+    static const char* const g_option_names[OPT_COUNT] = {"mxv_hub", "mxv_hub_min_count", "mxv_hub_total", "mxv_hub_smem", "mxv_l2_persist", "vxm_selbits", "mxv_phases", "mxv_phase_slots", "mxv_phase_only", "mxv_seg", "mxv_seg_min_density", "mxv_tail_range_log2", "small_front", "vxm_struct", "mxv_red", "mxv_row_classes", "mxv_row_min_count", "mxv_fixup_merge", "mxv_row_min_nnz", "mxv_bank_order", "mxv_reserve_sms", "mxv_pdl"};
     int64_t get_option(int opt) { return g_options[opt]; }
 
     void count_launch(int n) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }

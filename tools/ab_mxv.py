@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 from spla_b200 import graphs  # noqa: E402
 from spla_b200.backend import Backend  # noqa: E402
 
-DEFAULTS = {"mxv_hub": 1, "mxv_phase_slots": 45056, "mxv_phases": 4, "mxv_red": 1, "mxv_row_classes": 1, "mxv_row_min_count": 64, "mxv_tail_range_log2": 24, "mxv_phase_only": 0, "mxv_l2_persist": 0, "mxv_fixup_merge": 2, "mxv_row_min_nnz": 25165824, "mxv_bank_order": 1}
+DEFAULTS = {"mxv_hub": 1, "mxv_phase_slots": 45056, "mxv_phases": 4, "mxv_red": 1, "mxv_row_classes": 1, "mxv_row_min_count": 64, "mxv_tail_range_log2": 24, "mxv_phase_only": 0, "mxv_l2_persist": 0, "mxv_fixup_merge": 2, "mxv_row_min_nnz": 25165824, "mxv_bank_order": 1, "mxv_pdl": 1}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=24)
