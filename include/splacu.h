@@ -85,7 +85,9 @@ SPLACU_API int         splacu_launch_count(uint64_t* count); /* kernels launched
  * sums, then one thread per row in class order), 1 = one cooperative launch with a grid barrier per class, 0 = one launch per class;
  * 2 and 1 add in the same order (bit-identical results). "mxv_bank_order" (at handle creation, default 1) = permute the entries of a row
  * run inside a lane of a hub class against shared-memory bank conflicts. "mxv_reserve_sms" (per call, default 0) = SMs the persistent
- * class kernels leave free for the kernels of a collective running beside them.
+ * class kernels leave free for the kernels of a collective running beside them. "mxv_pdl" (per call, default 1) = the class passes of a
+ * whole product are launched with programmatic stream serialization (the next pass's CTAs load their hub table under the tail of the
+ * previous pass and wait, griddepcontrol.wait, before they touch r: same results).
  * A product on a handle with column classes forks the handle's side stream from the caller's stream and joins it before it returns
  * control of the stream (the mask-first CSR pass runs there): to the caller the call is still ordered on the one stream it passed.
  * Also from the environment: SPLACU_OPTIONS="name=value,..." */
